@@ -1,0 +1,115 @@
+/*
+ * orx.h -- C ABI of the B200 rollout engine (liborx.so).
+ *
+ * The reference has no FFI: the rollout seam is three plain Java calls made only from
+ * MCTSTree.simulation / backpropagation (src/com/mld46/oponn/MCTSTree.java:372-373,409-410)
+ * on boards built once per game (src/com/mld46/oponn/Oponn.java:106-110).  Each entry point
+ * below names the reference call(s) it replaces; INTEGRATION.md shows the Java (Panama FFM)
+ * and Python (ctypes) bindings a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer it passes; the
+ * library owns its device scratch.  Every function returns 0 on success or a negative
+ * ORX_E_* code (the reference throws unchecked exceptions instead -- SURVEY.md 8b).
+ * A context is bound to one CUDA device and one stream; calls on one context must not
+ * overlap, distinct contexts are independent.  There is no CPU fallback: without a usable
+ * CUDA device orx_create fails with ORX_E_CUDA.
+ */
+#ifndef ORX_H
+#define ORX_H
+
+#include "orx_state.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORX_OK            0
+#define ORX_E_INVALID    -1   /* bad argument / map / rules                               */
+#define ORX_E_CUDA       -2   /* CUDA runtime error (orx_last_error has the text)         */
+#define ORX_E_LEAF       -3   /* a leaf record failed validation (IllegalArgumentException
+                                 analogue of SimulationBoard.java:357,430)                */
+#define ORX_E_NOMEM      -4
+
+typedef struct OrxCtx OrxCtx;
+
+/* Replaces: new ModellingBoard(boardState, simAgents, cardManager, i, limit) x CORES
+ * (Oponn.java:106-110 -> SimulationBoard.java:102-139) and BattleSim's static table build
+ * (BattleSim.java:46-59).  Copies map and rules, stages them on `device`, builds the battle
+ * outcome tables for every (a, d) in 1..100 x 1..100 on the GPU.  All playout policies are
+ * SimRandom (lux_agent_modelling=false). */
+int orx_create(const OrxMap *map, const OrxRules *rules, int device, OrxCtx **out);
+
+/* Replaces: letting the boards be garbage collected. */
+void orx_destroy(OrxCtx *ctx);
+
+/* Text of the last error on this thread (never NULL). */
+const char *orx_last_error(void);
+
+/* Bytes per leaf record for this context (== orx_leaf_layout(N, P).stride). */
+int orx_leaf_stride(const OrxCtx *ctx);
+
+/* Replaces, batched and fused: for each leaf, `playouts_per_leaf` times
+ *     board.setupState(boardState); board.simulate();            (MCTSTree.java:372-373)
+ *     board.getPlayerOutOnTurn(); board.getSimTurnCount();       (MCTSTree.java:409-410)
+ * HOST buffers: leaves (n_leaves * stride bytes) are copied to the device, results are
+ * copied back before returning.  Playout k of leaf i uses stream (seed, game id
+ * first_game + i*playouts_per_leaf + k), so results do not depend on how a batch is split
+ * across calls, contexts or GPUs.  `agg` (n_leaves records) receives exact integer sums;
+ * `games` (n_leaves*playouts_per_leaf records) may be NULL. */
+int orx_rollout_batch(OrxCtx *ctx, const void *leaves, int n_leaves, int playouts_per_leaf,
+                      uint64_t seed, uint64_t first_game,
+                      OrxLeafResult *agg, OrxGameResult *games);
+
+/* Same, DEVICE buffers, asynchronous on the context's stream (use orx_sync).  `agg_dev`
+ * is overwritten (zeroed, then accumulated).  `games_dev` may be NULL. */
+int orx_rollout_batch_device(OrxCtx *ctx, const void *leaves_dev, int n_leaves, int playouts_per_leaf,
+                             uint64_t seed, uint64_t first_game,
+                             OrxLeafResult *agg_dev, OrxGameResult *games_dev);
+
+/* Replay of injected streams (the "identical injected dice/move stream" harness): game g
+ * plays leaf g with the explicit words words[g*words_per_game ...].  HOST buffers. */
+int orx_rollout_replay(OrxCtx *ctx, const void *leaves, int n_games,
+                       const uint32_t *words, uint32_t words_per_game, OrxGameResult *games);
+
+/* Block until everything queued on the context's stream has finished. */
+int orx_sync(OrxCtx *ctx);
+
+/* The CUDA stream (cudaStream_t) the context launches on, for event timing by the host. */
+void *orx_stream(OrxCtx *ctx);
+
+/* Milliseconds the last rollout kernel took on the device (CUDA events on the context's
+ * stream; valid after orx_sync or a host-buffer call), and how many kernels the context has
+ * launched since creation. */
+float    orx_last_kernel_ms(OrxCtx *ctx);
+uint64_t orx_kernel_launches(const OrxCtx *ctx);
+
+/* Replaces: BattleSim.getAttackOutcomes(a, d) (BattleSim.java:174-184) for 1 <= a,d <= 100.
+ * Rows are in the reference's order (descending probability, stable).  Returns the row count
+ * (<= a+d) or a negative error; arrays hold up to `cap` rows. */
+int orx_get_attack_outcomes(OrxCtx *ctx, int attackers, int defenders,
+                            float *probability, int32_t *attacker_losses, int32_t *defender_losses,
+                            int32_t *invading, int cap);
+
+/* Replaces: n calls of BattleSim.simulateBattle(a, d) (BattleSim.java:66-145); battle i draws
+ * from stream (seed, first_game + i).  HOST output buffers. */
+int orx_simulate_battles(OrxCtx *ctx, int attackers, int defenders, int n,
+                         uint64_t seed, uint64_t first_game,
+                         int32_t *attacker_losses, int32_t *defender_losses);
+
+/* Replaces: n calls of BattleSim.simulateIndividualBattle(a, d) (BattleSim.java:152-162). */
+int orx_simulate_individual(OrxCtx *ctx, int attackers, int defenders, int n,
+                            uint64_t seed, uint64_t first_game, int32_t *attacker_losses);
+
+/* Stream self-test: evaluates java.util.Random derivations on the device over stream
+ * (seed, game) or over explicit `words` (NULL = counter mode).  ops[i]: >0 nextInt(ops[i]);
+ * 0 nextDouble; -1 nextGaussian; -2 raw word.  out[i] receives the value as a double. */
+int orx_stream_draws(OrxCtx *ctx, uint64_t seed, uint64_t game, const uint32_t *words, uint32_t n_words,
+                     const int32_t *ops, int n_ops, double *out, uint32_t *pos_out, uint32_t *flags_out);
+
+/* Replaces: CardManager.getCardCashValue(pos) (CardManager.java:283-341) as the device sees it. */
+int orx_card_cash_value(OrxCtx *ctx, int pos, int32_t *value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORX_H */

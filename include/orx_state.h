@@ -1,0 +1,208 @@
+/*
+ * orx_state.h -- flat game-state encoding shared by every side of the rollout seam.
+ *
+ * One header, plain C, no CUDA types: included by the CUDA engine (oponn_b200/csrc),
+ * by the CPU oracle (oracle/), and mirrored byte-for-byte by the Java / Python hosts
+ * (INTEGRATION.md).  It replaces the Java object graph that crosses the seam in the
+ * reference:
+ *
+ *   BoardState                        src/com/mld46/oponn/BoardState.java:16-55
+ *   the Country[] it borrows          src/com/mld46/oponn/BoardState.java:118-139
+ *   CardManager's real hand / deck    src/com/mld46/oponn/CardManager.java:20-31,240-248
+ *   the board's result getters        src/com/mld46/oponn/sim/boards/SimulationBoard.java:1031-1044
+ *
+ * Everything is little-endian, naturally aligned, and position independent.
+ */
+#ifndef ORX_STATE_H
+#define ORX_STATE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef __CUDACC__
+#define ORX_HD __host__ __device__
+#else
+#define ORX_HD
+#endif
+
+/* ---- limits ------------------------------------------------------------ */
+#define ORX_MAX_TERRITORIES 252   /* card codes and list sizes (N+2) are bytes       */
+#define ORX_MAX_PLAYERS     8
+#define ORX_MAX_CONTINENTS  32
+#define ORX_MAX_DEGREE      32    /* out-neighbours per territory (one per lane)     */
+#define ORX_BONUS_ROUNDS    1024  /* rows of the per-round continent bonus table     */
+#define ORX_CARD_VALUES     1024  /* precomputed getCardCashValue(pos), pos < this   */
+#define ORX_MAX_ARMIES      (1 << 20)  /* per territory / placeable in a leaf record    */
+
+#define ORX_CARD_WILD   0xFFu     /* Card(-1,3): CardManager.java:14                 */
+#define ORX_OWNER_NONE  0xFFu     /* Country owner -1 (only before/during the draft) */
+
+/* SimulationBoard.Phase ordinals (SimulationBoard.java:19-27) */
+enum {
+    ORX_PHASE_COUNTRY_SELECTION = 0,
+    ORX_PHASE_INITIAL_PLACEMENT = 1,
+    ORX_PHASE_CARDS             = 2,
+    ORX_PHASE_PLACEMENT         = 3,
+    ORX_PHASE_ATTACK            = 4,
+    ORX_PHASE_FORTIFICATION     = 5,
+    ORX_PHASE_NEXT_PHASE        = 6
+};
+
+/* SimulationBoard.AttackState ordinals (SimulationBoard.java:29-35) */
+enum {
+    ORX_ATTACK_START   = 0,
+    ORX_ATTACK_EXECUTE = 1,
+    ORX_ATTACK_INVADE  = 2,
+    ORX_ATTACK_CASH    = 3,
+    ORX_ATTACK_PLACE   = 4
+};
+
+/* Card sets: com.sillysoft.lux.Card is not part of the reference repository (SDK jar, unpinned).
+ * DECLARED ASSUMPTION used by every implementation of this header: three cards are a set when one is a
+ * wildcard, or all three symbols are equal, or all three differ; Card.getRandomSet(hand) picks uniformly
+ * among the valid triples i<j<k of the hand, enumerated lexicographically, with one nextInt(count). */
+
+/* ---- static per-map / per-ruleset inputs ------------------------------- */
+
+/* The Country graph + board constants the SimulationBoard constructor captures
+ * (SimulationBoard.java:102-139).  CSR adjacency keeps Country.getAdjoiningList()
+ * ORDER: SimRandom picks "the j-th enemy neighbour in list order"
+ * (SimRandom.java:95-109), so the order is part of the semantics. */
+typedef struct OrxMap {
+    int32_t        n_territories;    /* numberOfCountries                        */
+    int32_t        n_continents;     /* numberOfContinents                       */
+    int32_t        n_players;        /* numberOfPlayers                          */
+    int32_t        reserved;
+    const int32_t *adj_offsets;      /* [n_territories+1]                        */
+    const int32_t *adj;              /* [adj_offsets[n]] neighbour codes         */
+    const int32_t *continent;        /* [n_territories] Country.getContinent()   */
+    const int32_t *continent_bonus;  /* [n_continents] initialContinentBonuses   */
+    const int32_t *card_symbol;      /* [n_territories] 0..2, or NULL = code % 3
+                                        (CardManager.java:54-61: counter cycles in
+                                        Country[] iteration order)               */
+} OrxMap;
+
+/* Game settings (BoardState.java:22-26) + engine limits. */
+typedef struct OrxRules {
+    int32_t     use_cards;
+    int32_t     transfer_cards;
+    int32_t     immediate_cash;       /* carried; compiled out in the reference
+                                         (SimulationBoard.java:852-855)          */
+    int32_t     continent_increase;   /* percent per round                       */
+    const char *card_progression;     /* Lux progression string, e.g.
+                                         "4, 6, 8, 10, 15, 20..."                */
+    int32_t     max_player_turns;     /* step cap; 0 = default (1<<16)           */
+    int32_t     reserved;
+} OrxRules;
+
+/* ---- the leaf record (one MCTS leaf = one rollout start state) --------- */
+
+/* Fixed 32-byte header followed by four byte arrays whose offsets depend only on
+ * (n_territories, n_players): see orx_leaf_layout().  Records in a batch are
+ * leaf_stride bytes apart (multiple of 16) so a warp loads one with 128-bit
+ * coalesced reads. */
+typedef struct OrxLeafHeader {
+    int32_t turn_count;        /* BoardState.turnCount -> simStartTurn               */
+    int32_t placeable;         /* BoardState.numberOfPlaceableArmies                 */
+    int16_t attacking_cc;      /* BoardState.attackingCC, -1 = none                  */
+    int16_t defending_cc;      /* BoardState.defendingCC, -1 = none                  */
+    int16_t card_pos;          /* CardManager.cardProgressionPos (CardManager.java:247) */
+    int8_t  current_player;    /* BoardState.currentPlayer                           */
+    int8_t  phase;             /* ORX_PHASE_*                                        */
+    int8_t  attack_state;      /* ORX_ATTACK_*                                       */
+    int8_t  has_invaded;       /* BoardState.hasInvadedACountry                      */
+    int8_t  defending_player;  /* BoardState.defendingPlayer, -1 = none              */
+    int8_t  attack_until_dead; /* the board's sticky attackUntilDead bit (SURVEY 8.1
+                                  quirk 2; SimulationBoard.java:93,754,763)          */
+    uint8_t n_hand;            /* |CardManager.inHand|: the real hand, handed to
+                                  whoever is current_player (SimulationBoard.java:215-218) */
+    uint8_t n_deck;            /* |CardManager.notInHand|: the unseen deck, in list order */
+    uint8_t reserved[10];
+} OrxLeafHeader;
+
+/* Leaf validity (engine contract; the reference would throw, loop or index out of bounds on
+ * most of these -- SimulationBoard.java:357,430; here the playout is flagged ORX_FLAG_ERROR):
+ *   0 <= current_player < P;  phase in COUNTRY_SELECTION..FORTIFICATION;  attack_state in START..PLACE;
+ *   -1 <= attacking_cc, defending_cc < N;  -1 <= defending_player < P;  card_pos >= 0;
+ *   |placeable| <= ORX_MAX_ARMIES;  n_hand + n_deck <= N + 2;  every card is a territory code or ORX_CARD_WILD;
+ *   every owner is < P (or ORX_OWNER_NONE while phase == COUNTRY_SELECTION);  1 <= armies[t] <= ORX_MAX_ARMIES.
+ * A flagged playout (ORX_FLAG_ERROR or ORX_FLAG_STREAM_END) reports only its flags: every other field
+ * of its OrxGameResult is zero. */
+typedef struct OrxLeafLayout {
+    int32_t off_owner;    /* uint8  owner[N]    : 0..P-1, ORX_OWNER_NONE            */
+    int32_t off_armies;   /* int32  armies[N]                                       */
+    int32_t off_ncards;   /* uint8  ncards[P]   : BoardState.playerNumberOfCards    */
+    int32_t off_cards;    /* uint8  cards[N+2]  : hand[0..n_hand) then deck[0..n_deck),
+                             each in Java List order; territory code or ORX_CARD_WILD */
+    int32_t stride;       /* bytes per record, multiple of 16                       */
+} OrxLeafLayout;
+
+static inline ORX_HD OrxLeafLayout orx_leaf_layout(int n_territories, int n_players)
+{
+    OrxLeafLayout l;
+    int off = (int)sizeof(OrxLeafHeader);
+    l.off_owner = off;   off += (n_territories + 3) & ~3;
+    l.off_armies = off;  off += 4 * n_territories;
+    l.off_ncards = off;  off += (n_players + 3) & ~3;
+    l.off_cards = off;   off += (n_territories + 2 + 3) & ~3;
+    l.stride = (off + 15) & ~15;
+    return l;
+}
+
+/* ---- results ----------------------------------------------------------- */
+
+#define ORX_FLAG_ERROR        1u  /* the Java board would have thrown (illegal state)    */
+#define ORX_FLAG_STEP_LIMIT   2u  /* max_player_turns reached before a terminal position */
+#define ORX_FLAG_STREAM_END   4u  /* an injected stream ran out of words                 */
+
+/* One playout: what MCTSTree.backpropagation reads from a board
+ * (MCTSTree.java:409-410) plus two trajectory pins used by the parity tests. */
+typedef struct OrxGameResult {
+    int32_t  player_out_on_turn[ORX_MAX_PLAYERS]; /* -1 winner / sim round eliminated / 0 */
+    int32_t  sim_turn_count;                      /* getSimTurnCount()                     */
+    uint32_t flags;                               /* ORX_FLAG_*                            */
+    uint32_t stream_pos;  /* 32-bit words drawn when the game became terminal            */
+    uint32_t board_hash;  /* sum over territories t of orx_mix(t, owner, armies) mod 2^32
+                             on the final board (order independent => lane parallel)  */
+} OrxGameResult;
+
+static inline ORX_HD uint32_t orx_mix(uint32_t t, uint32_t owner, uint32_t armies)
+{
+    uint32_t x = armies * 2654435761u ^ ((owner + 1u) * 0x85EBCA77u) ^ ((t + 1u) * 0xC2B2AE3Du);
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    return x;
+}
+
+/* Exact integer sums over the playouts of one leaf; every running mean that
+ * MCTSTree.backpropagation keeps (MCTSTree.java:412-427) is a ratio of these. */
+typedef struct OrxLeafResult {
+    int64_t n;                               /* playouts                              */
+    int64_t len_sum;                         /* sum of sim_turn_count                 */
+    int64_t wins[ORX_MAX_PLAYERS];           /* playouts with player_out_on_turn==-1  */
+    int64_t win_len_sum[ORX_MAX_PLAYERS];    /* sum of sim_turn_count over those      */
+    int64_t flagged;                         /* playouts with flags != 0              */
+    int64_t reserved;
+} OrxLeafResult;
+
+/* ---- the injected random stream ---------------------------------------- */
+/*
+ * Every random draw of a playout comes from ONE sequence of 32-bit words w_0, w_1, ...
+ * consumed in program order through java.util.Random's documented derivations
+ * (next(bits) = w >>> (32-bits); nextInt(bound); nextDouble(); nextGaussian()).
+ * A Java harness reproduces a playout by giving BattleSim.random, SimRandom.random,
+ * CardManager.random and Card.getRandomSet the same word source.
+ *
+ * Counter mode: w_i = Philox4x32-10( ctr = {32*(i/128) + i%32, 0, game_lo, game_hi},
+ *                                    key = {seed_lo, seed_hi} )[ (i/32) % 4 ]
+ * i.e. words come in blocks of 128: lane l of a warp evaluates counter 32*block+l once
+ * and the four outputs of all 32 lanes are consumed component-major.
+ * Replay mode: w_i = words[i] from a caller-supplied array.
+ */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORX_STATE_H */

@@ -1,0 +1,645 @@
+// orx_api.cu -- the C ABI of include/orx.h: context, tables, launches.  Plain CUDA runtime, no torch.
+//
+// There is no CPU fallback anywhere in this file: every entry point either runs its CUDA kernels or
+// returns ORX_E_CUDA / ORX_E_INVALID.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#define ORX_BLOCK_THREADS 128
+
+#include "../../include/orx.h"
+#include "orx_game.cuh"
+
+using namespace orx;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return set_err(ORX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char *orx_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// BattleSim outcome tables (O/BattleSim.java:190-286), built on the device at context creation.
+// One block per (a, d).  generateProbabilities' scatter sweep is restated as a gather: a cell's
+// contributions are added in the reference's source order (remA ascending, remD ascending), each
+// as an unfused float multiply followed by an unfused float add, so every float equals Java's.
+// ---------------------------------------------------------------------------------------------
+__constant__ float c_single[3][2][3] = {
+    { { 0.4167f, 0.5833f, 0.f }, { 0.2546f, 0.7454f, 0.f } },          // 1 v 1, 1 v 2   (O/BattleSim.java:15-19)
+    { { 0.5787f, 0.4213f, 0.f }, { 0.2276f, 0.3241f, 0.4483f } },     // 2 v 1, 2 v 2   (:21-26)
+    { { 0.6597f, 0.3403f, 0.f }, { 0.3717f, 0.3358f, 0.2926f } },     // 3 v 1, 3 v 2   (:28-33)
+};
+
+__device__ __forceinline__ float table_contrib(const float *last, int A, int D, int sa, int sd, int ta, int td)
+{
+    if (sa < 1 || sd < 1 || sa > A || sd > D) return 0.f;
+    int pa = sa < 3 ? sa : 3, pd = sd < 2 ? sd : 2, n = pa < pd ? pa : pd;
+    int x = sa - ta, y = sd - td;
+    if (x < 0 || y < 0 || x + y != n) return 0.f;
+    float v = last[sa * (D + 1) + sd];
+    if (v == 0.f) return 0.f;
+    return __fmul_rn(v, c_single[pa - 1][pd - 1][x]);
+}
+
+__global__ void __launch_bounds__(256) build_tables_kernel(uint32_t *meta, uint64_t *rows, float *probs)
+{
+    extern __shared__ float tsm[];
+    const int A = blockIdx.x / ORX_TABLE_LIMIT + 1, D = blockIdx.x % ORX_TABLE_LIMIT + 1;
+    const int RL = D + 1, cells = (A + 1) * RL;
+    float *last = tsm, *next = tsm + cells;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) last[c] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) last[A * RL + D] = 1.0f;
+    __syncthreads();
+    for (;;) {
+        int transient = 0;
+        for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+            int ta = c / RL, td = c % RL;
+            float acc = 0.f;
+            if (ta == 0 || td == 0) acc = last[c];  // an absorbing cell keeps its mass (added first: it is its own first source)
+            else if (last[c] != 0.f) transient = 1;
+            // sources in (a ascending, d ascending) order
+            acc = __fadd_rn(acc, table_contrib(last, A, D, ta, td + 1, ta, td));
+            acc = __fadd_rn(acc, table_contrib(last, A, D, ta, td + 2, ta, td));
+            acc = __fadd_rn(acc, table_contrib(last, A, D, ta + 1, td, ta, td));
+            acc = __fadd_rn(acc, table_contrib(last, A, D, ta + 1, td + 1, ta, td));
+            acc = __fadd_rn(acc, table_contrib(last, A, D, ta + 2, td, ta, td));
+            next[c] = acc;
+        }
+        int any = __syncthreads_or(transient);
+        float *t = last; last = next; next = t;
+        if (!any) break;
+    }
+    // candidates in (remA asc, remD asc) order: (0, q) for q <= D, then (q - D, 0)
+    __shared__ float s_p[2 * ORX_TABLE_LIMIT + 2];
+    __shared__ uint8_t s_code[2 * ORX_TABLE_LIMIT + 2];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int ncand = A + D + 1;
+    float *cand_p = next;  // scratch (the other sweep buffer)
+    for (int q = threadIdx.x; q < ncand; q += blockDim.x) cand_p[q] = q <= D ? last[0 * RL + q] : last[(q - D) * RL + 0];
+    __syncthreads();
+    for (int q = threadIdx.x; q < ncand; q += blockDim.x) {
+        float p = cand_p[q];
+        if (p != 0.f) {
+            int rank = 0;  // Collections.sort(reverseOrder()): descending probability, stable
+            for (int j = 0; j < ncand; j++) {
+                float pj = cand_p[j];
+                if (pj != 0.f && (pj > p || (pj == p && j < q))) rank++;
+            }
+            s_p[rank] = p;
+            s_code[rank] = q <= D ? (uint8_t)q : (uint8_t)(0x80 | (q - D));  // survivors; bit 7 = invading (remD == 0)
+            atomicAdd(&s_n, 1);
+        }
+    }
+    __syncthreads();
+    // row base: tables are laid out with capacity a + d each, (a, d) row-major
+    if (threadIdx.x == 0) {
+        uint32_t off = 0;
+        for (int a = 1; a < A; a++) off += (uint32_t)(ORX_TABLE_LIMIT * a + ORX_TABLE_LIMIT * (ORX_TABLE_LIMIT + 1) / 2);
+        for (int d = 1; d < D; d++) off += (uint32_t)(A + d);
+        int n = s_n;
+        double total = 0;
+        for (int i = 0; i < n; i++) {
+            total = __dadd_rn(total, (double)s_p[i]);                // "total += ao.probability" (O/BattleSim.java:132)
+            double scaled = __dmul_rn(total, 9007199254740992.0);    // exact: power of two
+            unsigned long long thr = (unsigned long long)scaled;     // r <= total  <=>  k <= floor(total * 2^53)
+            if (thr > 9007199254740991ull) thr = 9007199254740991ull;
+            rows[off + i] = (thr << 11) | (unsigned long long)s_code[i];
+            probs[off + i] = s_p[i];
+        }
+        meta[(A - 1) * ORX_TABLE_LIMIT + (D - 1)] = (off << 8) | (uint32_t)n;
+    }
+}
+
+static const int kTableRows = 2 * ORX_TABLE_LIMIT * (ORX_TABLE_LIMIT * (ORX_TABLE_LIMIT + 1) / 2);  // sum of a + d
+
+// ---------------------------------------------------------------------------------------------
+// small kernels behind the BattleSim / stream / card entry points
+// ---------------------------------------------------------------------------------------------
+__global__ void battles_kernel(const __grid_constant__ DevMap dm, int a, int d, int n, unsigned long long seed,
+                               unsigned long long first_game, int individual, int32_t *al_out, int32_t *dl_out)
+{
+    __shared__ uint32_t sm[4][128 + 8];
+    int wid = threadIdx.x >> 5;
+    long long i = (long long)blockIdx.x * 4 + wid;
+    if (i >= n) return;
+    Stream<false> s;
+    s.init(sm[wid] + 8, sm[wid], seed, first_game + (unsigned long long)i, nullptr, 0);
+    int al = 0, dl = 0;
+    if (individual) {
+        if (a < 1 || a > 3 || d < 1 || d > 2) s.flags |= ORX_FLAG_ERROR;
+        else al = single_roll(dm, a, d, s.next_k53());
+    } else if (a >= 1 && d >= 1) {
+        simulate_battle(dm, s, a, d, al, dl);
+    }
+    if (lane_id() == 0) { al_out[i] = al; if (dl_out) dl_out[i] = dl; }
+}
+
+template <bool REPLAY>
+__global__ void draws_kernel(unsigned long long seed, unsigned long long game, const uint32_t *words, uint32_t n_words,
+                             const int32_t *ops, int n_ops, double *out, uint32_t *pos_flags)
+{
+    __shared__ uint32_t sm[128 + 8];
+    Stream<REPLAY> s;
+    s.init(sm + 8, sm, seed, game, words, n_words);
+    for (int i = 0; i < n_ops; i++) {
+        int op = ops[i];
+        double v;
+        if (op > 0) v = (double)s.next_int(op);
+        else if (op == 0) v = s.next_double();
+        else if (op == -1) v = next_gaussian(s);
+        else v = (double)s.word();
+        if (lane_id() == 0) out[i] = v;
+    }
+    if (lane_id() == 0) { pos_flags[0] = s.pos; pos_flags[1] = s.flags; }
+}
+
+__global__ void card_value_kernel(const __grid_constant__ DevMap dm, int pos, int32_t *out)
+{
+    uint32_t flags = 0;
+    int v = card_cash_value(dm, pos, flags);
+    out[0] = v; out[1] = (int32_t)flags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct OrxCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevMap dm;
+    int nwt = 2;
+    int sm_count = 0;
+    int blocks_per_sm[2] = { 0, 0 };  // [replay]
+    size_t smem_bytes = 0;
+    uint8_t *d_blob = nullptr;
+    int32_t *d_bonus_table = nullptr, *d_card_table = nullptr;
+    uint32_t *d_meta = nullptr;
+    uint64_t *d_rows = nullptr;
+    float *d_probs = nullptr;
+    unsigned long long *d_ticket = nullptr;
+    // staging for the host-buffer entry points (grown on demand)
+    void *d_leaves = nullptr; size_t cap_leaves = 0;
+    void *d_agg = nullptr; size_t cap_agg = 0;
+    void *d_games = nullptr; size_t cap_games = 0;
+    void *d_words = nullptr; size_t cap_words = 0;
+    bool have_time = false;
+    uint64_t launches = 0;
+};
+
+static int ensure(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return ORX_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return ORX_OK;
+}
+
+// CardManager.getCardCashValue families (O/CardManager.java:283-341)
+static int parse_progression(const char *cp, double *exp_out, int *five)
+{
+    *exp_out = 1.0; *five = 0;
+    if (!cp) return PROG_UNKNOWN;
+    if (strchr(cp, '%')) {
+        const char *hat = strchr(cp, '^');
+        int pct = 0;
+        if (hat) {  // Integer.valueOf(cp.substring(cp.indexOf('^')+1, cp.length()-1))
+            std::string t(hat + 1);
+            if (!t.empty()) t.pop_back();
+            pct = atoi(t.c_str());
+        }
+        *five = cp[0] == '5';
+        *exp_out = 1 + (pct / 100.0);
+        return PROG_TABLE;
+    }
+    if (!strcmp(cp, "0")) return PROG_0;
+    if (!strcmp(cp, "5, 5, 5...")) return PROG_555;
+    if (!strcmp(cp, "4, 4, 6, 6, 6, 8, 8, 8, 8, 10...")) return PROG_4466688;
+    if (!strcmp(cp, "4, 5, 6...")) return PROG_456;
+    if (!strcmp(cp, "4, 6, 8...")) return PROG_468;
+    if (!strcmp(cp, "3, 6, 9...")) return PROG_369;
+    if (!strcmp(cp, "4, 6, 8, 10, 15, 20...")) return PROG_46810;
+    if (!strcmp(cp, "5, 10, 15...")) return PROG_51015;
+    if (!strcmp(cp, "4, 6, 8, 10, 15, 20, 25, 10, 10, 10...")) return PROG_4681015202510;
+    return PROG_UNKNOWN;
+}
+
+static int32_t java_d2i_host(double d)
+{
+    if (d != d) return 0;
+    if (d >= 2147483647.0) return 2147483647;
+    if (d <= -2147483648.0) return (int32_t)(-2147483647 - 1);
+    return (int32_t)d;
+}
+
+template <int NWT, bool REPLAY>
+static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<NWT, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rollout_kernel<NWT, REPLAY>, ORX_BLOCK_THREADS, smem);
+}
+
+extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, OrxCtx **out)
+{
+    if (!map || !rules || !out) return set_err(ORX_E_INVALID, "null argument");
+    *out = nullptr;
+    const int N = map->n_territories, C = map->n_continents, P = map->n_players;
+    if (N < 1 || N > ORX_MAX_TERRITORIES || P < 2 || P > ORX_MAX_PLAYERS || C < 1 || C > ORX_MAX_CONTINENTS)
+        return set_err(ORX_E_INVALID, "map dimensions out of range");
+    if (!map->adj_offsets || !map->adj || !map->continent || !map->continent_bonus)
+        return set_err(ORX_E_INVALID, "map arrays missing");
+    int maxdeg = 0;
+    if (map->adj_offsets[0] != 0) return set_err(ORX_E_INVALID, "adj_offsets[0] != 0");
+    for (int t = 0; t < N; t++) {
+        int dg = map->adj_offsets[t + 1] - map->adj_offsets[t];
+        if (dg < 0 || dg > ORX_MAX_DEGREE) return set_err(ORX_E_INVALID, "territory degree out of range");
+        if (dg > maxdeg) maxdeg = dg;
+        for (int e = map->adj_offsets[t]; e < map->adj_offsets[t + 1]; e++)
+            if (map->adj[e] < 0 || map->adj[e] >= N) return set_err(ORX_E_INVALID, "neighbour code out of range");
+        if (map->continent[t] < 0 || map->continent[t] >= C) return set_err(ORX_E_INVALID, "continent id out of range");
+        if (map->card_symbol && (map->card_symbol[t] < 0 || map->card_symbol[t] > 2)) return set_err(ORX_E_INVALID, "card symbol out of range");
+    }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(ORX_E_CUDA, "no CUDA device: this engine has no CPU path");
+    if (device < 0 || device >= ndev) return set_err(ORX_E_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+
+    OrxCtx *c = new OrxCtx();
+    c->device = device;
+    DevMap &dm = c->dm;
+    memset(&dm, 0, sizeof dm);
+    c->nwt = N <= 64 ? 2 : 8;
+    dm.N = N; dm.C = C; dm.P = P; dm.NW = c->nwt; dm.NP = 32 * c->nwt;
+    dm.degp = ((maxdeg > 0 ? maxdeg : 1) + 3) & ~3;
+    dm.cap = (N + 2 + 31) & ~31;
+    dm.use_cards = rules->use_cards != 0; dm.transfer_cards = rules->transfer_cards != 0;
+    dm.cont_inc = rules->continent_increase;
+    dm.max_turns = rules->max_player_turns > 0 ? rules->max_player_turns : (1 << 16);
+    dm.can_run_out = P * 5 > N + 2;  // O/CardManager.java:65
+    double pexp; int five;
+    dm.prog_family = parse_progression(rules->card_progression, &pexp, &five);
+    {   // calculateStartingArmies (SimulationBoard.java:518-533)
+        double f1 = N / 42.0; f1 -= 1.0; f1 /= 2.0; f1 += 1.0;
+        dm.start_armies = (int)floor(f1 * (50 - P * 5) + 0.5);
+    }
+    OrxLeafLayout L = orx_leaf_layout(N, P);
+    dm.leaf_stride = L.stride; dm.off_owner = L.off_owner; dm.off_armies = L.off_armies;
+    dm.off_ncards = L.off_ncards; dm.off_cards = L.off_cards;
+
+    // static map image
+    int off = 0;
+    dm.adj_off = off;  off += (N * dm.degp + 3) & ~3;
+    dm.deg_off = off;  off += dm.NP;
+    dm.sym_off = off;  off += dm.NP;
+    dm.nbr_off = off;  off += 4 * dm.NW * dm.NP;
+    dm.cont_off = off; off += 4 * C * dm.NW;
+    dm.bonus_off = off; off += 4 * C;
+    dm.blob_bytes = (off + 15) & ~15;
+    std::vector<uint8_t> blob((size_t)dm.blob_bytes, 0);
+    uint32_t *nbr = (uint32_t *)(blob.data() + dm.nbr_off), *cont = (uint32_t *)(blob.data() + dm.cont_off);
+    int32_t *bonus = (int32_t *)(blob.data() + dm.bonus_off);
+    for (int t = 0; t < N; t++) {
+        int dg = map->adj_offsets[t + 1] - map->adj_offsets[t];
+        blob[dm.deg_off + t] = (uint8_t)dg;
+        for (int j = 0; j < dg; j++) {
+            int x = map->adj[map->adj_offsets[t] + j];
+            blob[dm.adj_off + t * dm.degp + j] = (uint8_t)x;
+            nbr[(x >> 5) * dm.NP + t] |= 1u << (x & 31);
+        }
+        int sym = map->card_symbol ? map->card_symbol[t] : t % 3;  // O/CardManager.java:54-61
+        blob[dm.sym_off + t] = (uint8_t)(1u << sym);
+        cont[map->continent[t] * dm.NW + (t >> 5)] |= 1u << (t & 31);
+    }
+    for (int i = 0; i < C; i++) bonus[i] = map->continent_bonus[i];
+
+    // per-warp dynamic slice
+    off = ORX_WARP_HDR_BYTES;
+    dm.w_rng = off;    off += 512;
+    dm.w_armies = off; off += 4 * dm.NP;
+    dm.w_owner = off;  off += dm.NP;
+    dm.w_alist = off;  off += dm.cap;
+    dm.w_cards = off;  off += (P + 1) * dm.cap;
+    dm.w_bytes = (off + 15) & ~15;
+    c->smem_bytes = (size_t)dm.blob_bytes + (size_t)(ORX_BLOCK_THREADS / 32) * (size_t)dm.w_bytes;
+
+    // single-roll thresholds: floor(cdf * 2^53) of O/BattleSim.java:36-44 (float sums widened to double)
+    {
+        const float a1_d1_al0 = 0.4167f, a1_d2_al0 = 0.2546f, a2_d1_al0 = 0.5787f, a2_d2_al0 = 0.2276f, a2_d2_al1 = 0.3241f,
+                    a3_d1_al0 = 0.6597f, a3_d2_al0 = 0.3717f, a3_d2_al1 = 0.3358f;
+        const double rows[6][2] = { { a1_d1_al0, 1.0 }, { a1_d2_al0, 1.0 }, { a2_d1_al0, 1.0 },
+                                    { a2_d2_al0, (float)(a2_d2_al0 + a2_d2_al1) }, { a3_d1_al0, 1.0 },
+                                    { a3_d2_al0, (float)(a3_d2_al0 + a3_d2_al1) } };
+        for (int r = 0; r < 6; r++)
+            for (int k = 0; k < 2; k++) dm.single_thr[r][k] = (uint64_t)(rows[r][k] * 9007199254740992.0);
+    }
+
+#define CKC(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) { set_err(ORX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); orx_destroy(c); return ORX_E_CUDA; } \
+    } while (0)
+
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&c->ev0));
+    CKC(cudaEventCreate(&c->ev1));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+
+    CKC(cudaMalloc(&c->d_blob, blob.size()));
+    CKC(cudaMemcpyAsync(c->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+    dm.blob = c->d_blob;
+    if (dm.cont_inc != 0) {  // recalculateContinentBonuses (SimulationBoard.java:956-963), one row per exponent
+        std::vector<int32_t> tab((size_t)ORX_BONUS_ROUNDS * C);
+        for (int e = 0; e < ORX_BONUS_ROUNDS; e++) {
+            double factor = pow(1 + dm.cont_inc / 100.0, (double)e);
+            for (int i = 0; i < C; i++) tab[(size_t)e * C + i] = java_d2i_host(floor(map->continent_bonus[i] * factor));
+        }
+        CKC(cudaMalloc(&c->d_bonus_table, tab.size() * 4));
+        CKC(cudaMemcpy(c->d_bonus_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        dm.bonus_table = c->d_bonus_table;
+    }
+    if (dm.prog_family == PROG_TABLE) {  // exponential progressions (O/CardManager.java:287-305)
+        std::vector<int32_t> tab(ORX_CARD_VALUES);
+        for (int pos = 0; pos < ORX_CARD_VALUES; pos++) {
+            int base, offset;
+            if (five) { base = 5 * pos; offset = 6; } else { base = pos <= 4 ? 2 * (pos + 1) : 5 * (pos - 2); offset = 8; }
+            tab[pos] = java_d2i_host(floor(base <= 25 ? (double)base : base * pow(pexp, (double)(pos - offset))));
+        }
+        CKC(cudaMalloc(&c->d_card_table, tab.size() * 4));
+        CKC(cudaMemcpy(c->d_card_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        dm.card_table = c->d_card_table;
+    }
+    CKC(cudaMalloc(&c->d_meta, sizeof(uint32_t) * ORX_TABLE_LIMIT * ORX_TABLE_LIMIT));
+    CKC(cudaMalloc(&c->d_rows, sizeof(uint64_t) * kTableRows));
+    CKC(cudaMalloc(&c->d_probs, sizeof(float) * kTableRows));
+    CKC(cudaMalloc(&c->d_ticket, sizeof(unsigned long long)));
+    dm.bt_meta = c->d_meta; dm.bt_rows = c->d_rows;
+    {
+        size_t tsm = 2 * sizeof(float) * (ORX_TABLE_LIMIT + 1) * (ORX_TABLE_LIMIT + 1);
+        CKC(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        build_tables_kernel<<<ORX_TABLE_LIMIT * ORX_TABLE_LIMIT, 256, tsm, c->stream>>>(c->d_meta, c->d_rows, c->d_probs);
+        CKC(cudaGetLastError());
+        c->launches++;
+    }
+    if (c->nwt == 2) {
+        CKC((configure_kernel<2, false>(c->smem_bytes, &c->blocks_per_sm[0])));
+        CKC((configure_kernel<2, true>(c->smem_bytes, &c->blocks_per_sm[1])));
+    } else {
+        CKC((configure_kernel<8, false>(c->smem_bytes, &c->blocks_per_sm[0])));
+        CKC((configure_kernel<8, true>(c->smem_bytes, &c->blocks_per_sm[1])));
+    }
+    if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) { set_err(ORX_E_CUDA, "rollout kernel does not fit on an SM"); orx_destroy(c); return ORX_E_CUDA; }
+    CKC(cudaStreamSynchronize(c->stream));
+#undef CKC
+    *out = c;
+    return ORX_OK;
+}
+
+extern "C" void orx_destroy(OrxCtx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_blob); cudaFree(c->d_bonus_table); cudaFree(c->d_card_table); cudaFree(c->d_meta);
+    cudaFree(c->d_rows); cudaFree(c->d_probs); cudaFree(c->d_ticket);
+    cudaFree(c->d_leaves); cudaFree(c->d_agg); cudaFree(c->d_games); cudaFree(c->d_words);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int orx_leaf_stride(const OrxCtx *c) { return c ? c->dm.leaf_stride : ORX_E_INVALID; }
+extern "C" void *orx_stream(OrxCtx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t orx_kernel_launches(const OrxCtx *c) { return c ? c->launches : 0; }
+
+extern "C" int orx_sync(OrxCtx *c)
+{
+    if (!c) return set_err(ORX_E_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORX_OK;
+}
+
+extern "C" float orx_last_kernel_ms(OrxCtx *c)
+{
+    if (!c || !c->have_time) return -1.f;
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+// one launch of the rollout kernel on the context's stream, bracketed by the timing events
+static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar)
+{
+    CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), c->stream));
+    unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[replay] * (ORX_BLOCK_THREADS / 32);
+    unsigned long long need = (ar.total + (ORX_BLOCK_THREADS / 32) - 1) / (ORX_BLOCK_THREADS / 32);
+    unsigned long long blocks = warps / (ORX_BLOCK_THREADS / 32);
+    if (need < blocks) blocks = need;
+    if (blocks == 0) blocks = 1;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    dim3 grid((unsigned)blocks), block(ORX_BLOCK_THREADS);
+    if (c->nwt == 2) {
+        if (replay) rollout_kernel<2, true><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+        else rollout_kernel<2, false><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+    } else {
+        if (replay) rollout_kernel<8, true><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+        else rollout_kernel<8, false><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->have_time = true;
+    c->launches++;
+    return ORX_OK;
+}
+
+extern "C" int orx_rollout_batch_device(OrxCtx *c, const void *leaves_dev, int n_leaves, int playouts_per_leaf,
+                                        uint64_t seed, uint64_t first_game, OrxLeafResult *agg_dev, OrxGameResult *games_dev)
+{
+    if (!c || !leaves_dev || n_leaves < 0 || playouts_per_leaf < 0) return set_err(ORX_E_INVALID, "bad argument");
+    if (!agg_dev && !games_dev) return set_err(ORX_E_INVALID, "no output buffer");
+    CK(cudaSetDevice(c->device));
+    if (agg_dev) CK(cudaMemsetAsync(agg_dev, 0, sizeof(OrxLeafResult) * (size_t)n_leaves, c->stream));
+    RolloutArgs ar;
+    memset(&ar, 0, sizeof ar);
+    ar.leaves = (const uint8_t *)leaves_dev; ar.n_leaves = n_leaves; ar.playouts_per_leaf = playouts_per_leaf;
+    ar.total = (unsigned long long)n_leaves * (unsigned long long)playouts_per_leaf;
+    ar.seed = seed; ar.first_game = first_game; ar.agg = agg_dev; ar.games = games_dev; ar.ticket = c->d_ticket;
+    if (ar.total == 0) return ORX_OK;
+    return launch_rollout(c, false, ar);
+}
+
+extern "C" int orx_rollout_batch(OrxCtx *c, const void *leaves, int n_leaves, int playouts_per_leaf, uint64_t seed,
+                                 uint64_t first_game, OrxLeafResult *agg, OrxGameResult *games)
+{
+    if (!c || !leaves || n_leaves < 0 || playouts_per_leaf < 0) return set_err(ORX_E_INVALID, "bad argument");
+    if (!agg && !games) return set_err(ORX_E_INVALID, "no output buffer");
+    CK(cudaSetDevice(c->device));
+    size_t total = (size_t)n_leaves * (size_t)playouts_per_leaf;
+    size_t lbytes = (size_t)n_leaves * (size_t)c->dm.leaf_stride;
+    int rc;
+    if ((rc = ensure(&c->d_leaves, &c->cap_leaves, lbytes ? lbytes : 16)) != ORX_OK) return rc;
+    if ((rc = ensure(&c->d_agg, &c->cap_agg, sizeof(OrxLeafResult) * (size_t)(n_leaves ? n_leaves : 1))) != ORX_OK) return rc;
+    if (games && (rc = ensure(&c->d_games, &c->cap_games, sizeof(OrxGameResult) * (total ? total : 1))) != ORX_OK) return rc;
+    CK(cudaMemcpyAsync(c->d_leaves, leaves, lbytes, cudaMemcpyHostToDevice, c->stream));
+    rc = orx_rollout_batch_device(c, c->d_leaves, n_leaves, playouts_per_leaf, seed, first_game,
+                                  (OrxLeafResult *)c->d_agg, games ? (OrxGameResult *)c->d_games : nullptr);
+    if (rc != ORX_OK) return rc;
+    if (agg) CK(cudaMemcpyAsync(agg, c->d_agg, sizeof(OrxLeafResult) * (size_t)n_leaves, cudaMemcpyDeviceToHost, c->stream));
+    if (games) CK(cudaMemcpyAsync(games, c->d_games, sizeof(OrxGameResult) * total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORX_OK;
+}
+
+extern "C" int orx_rollout_replay(OrxCtx *c, const void *leaves, int n_games, const uint32_t *words, uint32_t words_per_game,
+                                  OrxGameResult *games)
+{
+    if (!c || !leaves || !games || n_games < 0 || (!words && words_per_game)) return set_err(ORX_E_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    size_t lbytes = (size_t)n_games * (size_t)c->dm.leaf_stride, wbytes = (size_t)n_games * words_per_game * 4;
+    int rc;
+    if ((rc = ensure(&c->d_leaves, &c->cap_leaves, lbytes ? lbytes : 16)) != ORX_OK) return rc;
+    if ((rc = ensure(&c->d_words, &c->cap_words, wbytes ? wbytes : 16)) != ORX_OK) return rc;
+    if ((rc = ensure(&c->d_games, &c->cap_games, sizeof(OrxGameResult) * (size_t)(n_games ? n_games : 1))) != ORX_OK) return rc;
+    if (n_games == 0) return ORX_OK;
+    CK(cudaMemcpyAsync(c->d_leaves, leaves, lbytes, cudaMemcpyHostToDevice, c->stream));
+    if (wbytes) CK(cudaMemcpyAsync(c->d_words, words, wbytes, cudaMemcpyHostToDevice, c->stream));
+    RolloutArgs ar;
+    memset(&ar, 0, sizeof ar);
+    ar.leaves = (const uint8_t *)c->d_leaves; ar.n_leaves = n_games; ar.playouts_per_leaf = 1; ar.total = (unsigned long long)n_games;
+    ar.games = (OrxGameResult *)c->d_games; ar.ticket = c->d_ticket;
+    ar.words = (const uint32_t *)c->d_words; ar.words_per_game = words_per_game;
+    if ((rc = launch_rollout(c, true, ar)) != ORX_OK) return rc;
+    CK(cudaMemcpyAsync(games, c->d_games, sizeof(OrxGameResult) * (size_t)n_games, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORX_OK;
+}
+
+extern "C" int orx_get_attack_outcomes(OrxCtx *c, int a, int d, float *probability, int32_t *attacker_losses,
+                                       int32_t *defender_losses, int32_t *invading, int cap)
+{
+    if (!c || a < 1 || d < 1 || a > ORX_TABLE_LIMIT || d > ORX_TABLE_LIMIT || cap < 0) return set_err(ORX_E_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    uint32_t meta;
+    CK(cudaMemcpy(&meta, c->d_meta + (a - 1) * ORX_TABLE_LIMIT + (d - 1), 4, cudaMemcpyDeviceToHost));
+    int n = (int)(meta & 0xFFu);
+    std::vector<uint64_t> rows((size_t)(n ? n : 1));
+    std::vector<float> pr((size_t)(n ? n : 1));
+    if (n) {
+        CK(cudaMemcpy(rows.data(), c->d_rows + (meta >> 8), sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pr.data(), c->d_probs + (meta >> 8), sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < n && i < cap; i++) {
+        int code = (int)(rows[i] & 0xFFu), rem = code & 0x7F, inv = code >> 7;
+        if (probability) probability[i] = pr[i];
+        if (attacker_losses) attacker_losses[i] = inv ? a - rem : a;
+        if (defender_losses) defender_losses[i] = inv ? d : d - rem;
+        if (invading) invading[i] = inv;
+    }
+    return n;
+}
+
+static int run_battles(OrxCtx *c, int a, int d, int n, uint64_t seed, uint64_t first_game, int individual, int32_t *al, int32_t *dl)
+{
+    if (!c || n < 0 || !al) return set_err(ORX_E_INVALID, "bad argument");
+    if (n == 0) return ORX_OK;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(&c->d_games, &c->cap_games, sizeof(int32_t) * 2 * (size_t)n)) != ORX_OK) return rc;
+    int32_t *d_al = (int32_t *)c->d_games, *d_dl = d_al + n;
+    battles_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(c->dm, a, d, n, seed, first_game, individual, d_al, dl ? d_dl : nullptr);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpyAsync(al, d_al, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (dl) CK(cudaMemcpyAsync(dl, d_dl, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORX_OK;
+}
+
+extern "C" int orx_simulate_battles(OrxCtx *c, int a, int d, int n, uint64_t seed, uint64_t first_game, int32_t *al, int32_t *dl)
+{
+    if (!dl) return set_err(ORX_E_INVALID, "bad argument");
+    return run_battles(c, a, d, n, seed, first_game, 0, al, dl);
+}
+
+extern "C" int orx_simulate_individual(OrxCtx *c, int a, int d, int n, uint64_t seed, uint64_t first_game, int32_t *al)
+{
+    if (a < 1 || a > 3 || d < 1 || d > 2) return set_err(ORX_E_INVALID, "simulateIndividualBattle needs 1..3 attackers and 1..2 defenders");
+    return run_battles(c, a, d, n, seed, first_game, 1, al, nullptr);
+}
+
+extern "C" int orx_stream_draws(OrxCtx *c, uint64_t seed, uint64_t game, const uint32_t *words, uint32_t n_words,
+                                const int32_t *ops, int n_ops, double *out, uint32_t *pos_out, uint32_t *flags_out)
+{
+    if (!c || !ops || !out || n_ops < 0) return set_err(ORX_E_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    size_t need = 8 * (size_t)n_ops + 4 * (size_t)n_ops + 4 * (size_t)n_words + 64;
+    int rc;
+    if ((rc = ensure(&c->d_words, &c->cap_words, need)) != ORX_OK) return rc;
+    uint8_t *base = (uint8_t *)c->d_words;
+    double *d_out = (double *)base;
+    uint32_t *d_pf = (uint32_t *)(base + 8 * (size_t)n_ops);
+    int32_t *d_ops = (int32_t *)(base + 8 * (size_t)n_ops + 16);
+    uint32_t *d_w = (uint32_t *)(base + 8 * (size_t)n_ops + 16 + 4 * (size_t)n_ops);
+    CK(cudaMemcpyAsync(d_ops, ops, 4 * (size_t)n_ops, cudaMemcpyHostToDevice, c->stream));
+    if (words) {
+        if (n_words) CK(cudaMemcpyAsync(d_w, words, 4 * (size_t)n_words, cudaMemcpyHostToDevice, c->stream));
+        draws_kernel<true><<<1, 32, 0, c->stream>>>(seed, game, d_w, n_words, d_ops, n_ops, d_out, d_pf);
+    } else {
+        draws_kernel<false><<<1, 32, 0, c->stream>>>(seed, game, nullptr, 0, d_ops, n_ops, d_out, d_pf);
+    }
+    CK(cudaGetLastError());
+    c->launches++;
+    uint32_t pf[2];
+    CK(cudaMemcpyAsync(out, d_out, 8 * (size_t)n_ops, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(pf, d_pf, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (pos_out) *pos_out = pf[0];
+    if (flags_out) *flags_out = pf[1];
+    return ORX_OK;
+}
+
+extern "C" int orx_card_cash_value(OrxCtx *c, int pos, int32_t *value)
+{
+    if (!c || !value) return set_err(ORX_E_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(&c->d_agg, &c->cap_agg, 64)) != ORX_OK) return rc;
+    card_value_kernel<<<1, 1, 0, c->stream>>>(c->dm, pos, (int32_t *)c->d_agg);
+    CK(cudaGetLastError());
+    c->launches++;
+    int32_t v[2];
+    CK(cudaMemcpyAsync(v, c->d_agg, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (v[1]) return set_err(ORX_E_INVALID, "progression position outside the device table");
+    *value = v[0];
+    return ORX_OK;
+}

@@ -1,0 +1,395 @@
+// orx_device.cuh -- device-side building blocks of the rollout engine (sm_100a).
+//
+// One warp plays one game.  Everything a game mutates lives in that warp's slice of shared
+// memory or in lane-distributed registers; all control flow is warp-uniform; lane-parallel
+// work (board scans, defender selection, CDF search, dice batches, Philox) uses ballot /
+// shuffle / redux.  Randomness is the injected word stream of include/orx_state.h consumed
+// through java.util.Random's derivations, so a Java harness can replay a playout bit for bit.
+//
+// Reference files restated here (O/ = /root/reference/src/com/mld46/oponn/):
+//   O/BattleSim.java (whole), O/CardManager.java:283-341 ; the game itself is in orx_game.cuh
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orx_state.h"
+
+#define ORX_FULL 0xFFFFFFFFu
+#define ORX_TABLE_LIMIT 100
+
+namespace orx {
+
+// Card progression families (CardManager.getCardCashValue, O/CardManager.java:283-341)
+enum { PROG_UNKNOWN = 0, PROG_0, PROG_555, PROG_4466688, PROG_456, PROG_468, PROG_369, PROG_46810, PROG_51015,
+       PROG_4681015202510, PROG_TABLE };
+
+// Everything static a kernel needs, passed by value (constant bank).  `blob` is a byte image of
+// the map staged into shared memory once per block; the *_off fields are byte offsets into it.
+struct DevMap {
+    int32_t N, C, P, NW;        // territories, continents, players, 32-lane words per board scan
+    int32_t NP;                 // N rounded up to 32*NW
+    int32_t degp;               // bytes per adjacency row (max out-degree rounded up to 4)
+    int32_t cap;                // capacity of a card list = N+2 rounded up to 32
+    int32_t use_cards, transfer_cards, cont_inc, prog_family, max_turns, can_run_out;
+    int32_t blob_bytes;         // multiple of 16
+    int32_t adj_off;            // u8  [N][degp]   Country.getAdjoiningList() order
+    int32_t deg_off;            // u8  [NP]
+    int32_t sym_off;            // u8  [NP]        1 << card symbol of the territory card
+    int32_t nbr_off;            // u32 [NW][NP]    neighbour bitmask of territory t, word-major
+    int32_t cont_off;           // u32 [C][NW]     member bitmask of continent c
+    int32_t bonus_off;          // i32 [C]         initialContinentBonuses
+    // per-warp dynamic slice (bytes from the slice base)
+    int32_t w_rng, w_armies, w_owner, w_alist, w_cards, w_bytes;
+    int32_t leaf_stride, off_owner, off_armies, off_ncards, off_cards;
+    int32_t start_armies;       // calculateStartingArmies base (SimulationBoard.java:518-533)
+    const uint8_t  *blob;       // global copy of the static map image
+    const int32_t  *bonus_table;  // [ORX_BONUS_ROUNDS][C] when cont_inc != 0, else null
+    const int32_t  *card_table;   // [ORX_CARD_VALUES] for the exponential progressions, else null
+    const uint32_t *bt_meta;    // [100*100] (row offset << 8) | row count   for (a,d)
+    const uint64_t *bt_rows;    // (min(floor(cdf * 2^53), 2^53-1) << 11) | invading << 7 | survivors
+    uint64_t single_thr[6][2];  // floor(cdf*2^53) of BattleSim.outcomes rows (O/BattleSim.java:36-44)
+};
+
+// per-warp header words (uint32 indices into the first 32 bytes of the slice)
+enum { WH_GAUSS_LO = 0, WH_GAUSS_HI = 1, WH_HAVE_GAUSS = 2, WH_G0 = 3, WH_G1 = 4, WH_SIM_START = 5, WH_REM_COUNTRIES = 6 };
+#define ORX_WARP_HDR_BYTES 32
+
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31); }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// index of the n-th (0-based) set bit of a warp-uniform mask; n < popc(mask)
+__device__ __forceinline__ int nth_bit(uint32_t mask, int n)
+{
+    uint32_t hit = __ballot_sync(ORX_FULL, ((mask >> lane_id()) & 1u) && __popc(mask & lanemask_lt()) == n);
+    return __ffs(hit) - 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// all 32 lanes evaluate one Philox counter each: 128 words, component-major (orx_state.h)
+__device__ __noinline__ void philox_refill(uint32_t *buf, uint32_t blk, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1)
+{
+    uint32_t o[4];
+    int l = lane_id();
+    philox4x32_10(blk * 32u + (uint32_t)l, 0u, g0, g1, k0, k1, o);
+    __syncwarp();
+    buf[l] = o[0]; buf[32 + l] = o[1]; buf[64 + l] = o[2]; buf[96 + l] = o[3];
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+// The injected word stream of one game + java.util.Random's derivations
+// ---------------------------------------------------------------------------------------
+template <bool REPLAY>
+struct Stream {
+    uint32_t *buf;          // this warp's 128-word block in shared memory
+    uint32_t *hdr;          // this warp's header words (game id, cached gaussian)
+    uint32_t  pos;          // words consumed
+    int32_t   block;        // block index held in buf, -1 = none
+    uint32_t  k0, k1;       // Philox key = seed (kernel parameter, warp-uniform)
+    const uint32_t *words;  // REPLAY: explicit words
+    uint32_t  n_words;
+    uint32_t  flags;        // ORX_FLAG_* raised by the stream (and by the game)
+
+    __device__ __forceinline__ void init(uint32_t *b, uint32_t *h, uint64_t seed, uint64_t game, const uint32_t *w, uint32_t nw)
+    {
+        buf = b; hdr = h; pos = 0; block = -1; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        words = w; n_words = nw; flags = 0;
+        __syncwarp();
+        if (lane_id() == 0) { h[WH_G0] = (uint32_t)game; h[WH_G1] = (uint32_t)(game >> 32); h[WH_HAVE_GAUSS] = 0u; }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void refill(int32_t blk)
+    {
+        philox_refill(buf, (uint32_t)blk, hdr[WH_G0], hdr[WH_G1], k0, k1);
+        block = blk;
+    }
+
+    __device__ __forceinline__ uint32_t word()
+    {
+        uint32_t i = pos++;
+        if (REPLAY) {
+            if (i >= n_words) { flags |= ORX_FLAG_STREAM_END; return 0u; }
+            return __ldg(words + i);
+        }
+        int32_t blk = (int32_t)(i >> 7);
+        if (blk != block) refill(blk);
+        return buf[i & 127u];
+    }
+
+    // java.util.Random.nextInt(int bound)
+    __device__ __forceinline__ int next_int(int bound)
+    {
+        if (bound <= 0) { flags |= ORX_FLAG_ERROR; return 0; }
+        uint32_t u = word() >> 1;
+        uint32_t m = (uint32_t)bound - 1u;
+        if (((uint32_t)bound & m) == 0u) return (int)(((unsigned long long)(uint32_t)bound * u) >> 31);
+        for (;;) {
+            uint32_t r = u % (uint32_t)bound;
+            if ((int)(u - r + m) >= 0) return (int)r;
+            if (flags) return 0;
+            u = word() >> 1;
+        }
+    }
+
+    // the 53-bit integer k of java.util.Random.nextDouble() == k * 2^-53
+    __device__ __forceinline__ uint64_t next_k53()
+    {
+        uint64_t hi = word() >> 6;
+        uint64_t lo = word() >> 5;
+        return (hi << 27) + lo;
+    }
+    __device__ __forceinline__ double next_double() { return (double)(long long)next_k53() * 0x1.0p-53; }
+};
+
+// StrictMath.log == fdlibm __ieee754_log, restated with explicitly unfused IEEE operations.
+__device__ __noinline__ double fdlibm_log(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
+                 Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01, Lg7 = 1.479819860511658591e-01;
+#define M(a, b) __dmul_rn((a), (b))
+#define A(a, b) __dadd_rn((a), (b))
+#define S(a, b) __dsub_rn((a), (b))
+    int hx = __double2hiint(x);
+    uint32_t lx = (uint32_t)__double2loint(x);
+    int k = 0, i, j;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return __longlong_as_double(0xFFF0000000000000ll);
+        if (hx < 0) return __longlong_as_double(0x7FF8000000000000ll);
+        k -= 54; x = M(x, two54); hx = __double2hiint(x);
+    }
+    if (hx >= 0x7ff00000) return A(x, x);
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    i = (hx + 0x95f64) & 0x100000;
+    x = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x));
+    k += (i >> 20);
+    double f = S(x, 1.0), dk, R;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) { if (k == 0) return 0.0; dk = (double)k; return A(M(dk, ln2_hi), M(dk, ln2_lo)); }
+        R = M(M(f, f), S(0.5, M(0.33333333333333333, f)));
+        if (k == 0) return S(f, R);
+        dk = (double)k; return S(M(dk, ln2_hi), S(S(R, M(dk, ln2_lo)), f));
+    }
+    double s = __ddiv_rn(f, A(2.0, f));
+    dk = (double)k;
+    double z = M(s, s);
+    i = hx - 0x6147a;
+    double w = M(z, z);
+    j = 0x6b851 - hx;
+    double t1 = M(w, A(Lg2, M(w, A(Lg4, M(w, Lg6)))));
+    double t2 = M(z, A(Lg1, M(w, A(Lg3, M(w, A(Lg5, M(w, Lg7)))))));
+    i |= j;
+    R = A(t2, t1);
+    if (i > 0) {
+        double hfsq = M(M(0.5, f), f);
+        if (k == 0) return S(f, S(hfsq, M(s, A(hfsq, R))));
+        return S(M(dk, ln2_hi), S(S(hfsq, A(M(s, A(hfsq, R)), M(dk, ln2_lo))), f));
+    }
+    if (k == 0) return S(f, M(s, S(f, R)));
+    return S(M(dk, ln2_hi), S(S(M(s, S(f, R)), M(dk, ln2_lo)), f));
+#undef M
+#undef A
+#undef S
+}
+
+// The arithmetic half of java.util.Random.nextGaussian() (Marsaglia polar method): from an
+// accepted pair (v1, v2, q) to (first value, cached second value).
+__device__ __noinline__ double gaussian_from_pair(double v1, double v2, double q, double *second)
+{
+    double multiplier = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, fdlibm_log(q)), q));
+    *second = __dmul_rn(v2, multiplier);
+    return __dmul_rn(v1, multiplier);
+}
+
+// java.util.Random.nextGaussian(): second value cached per playout (in the warp header)
+template <bool REPLAY>
+__device__ __forceinline__ double next_gaussian(Stream<REPLAY> &s)
+{
+    if (s.hdr[WH_HAVE_GAUSS]) {
+        double g = __hiloint2double((int)s.hdr[WH_GAUSS_HI], (int)s.hdr[WH_GAUSS_LO]);
+        __syncwarp();
+        if (lane_id() == 0) s.hdr[WH_HAVE_GAUSS] = 0u;
+        __syncwarp();
+        return g;
+    }
+    double v1, v2, q;
+    do {
+        v1 = __dsub_rn(__dmul_rn(2.0, s.next_double()), 1.0);
+        v2 = __dsub_rn(__dmul_rn(2.0, s.next_double()), 1.0);
+        q = __dadd_rn(__dmul_rn(v1, v1), __dmul_rn(v2, v2));
+        if (s.flags) return 0.0;
+    } while (q >= 1.0 || q == 0.0);
+    double second;
+    double first = gaussian_from_pair(v1, v2, q, &second);
+    __syncwarp();
+    if (lane_id() == 0) {
+        s.hdr[WH_GAUSS_LO] = (uint32_t)__double2loint(second); s.hdr[WH_GAUSS_HI] = (uint32_t)__double2hiint(second);
+        s.hdr[WH_HAVE_GAUSS] = 1u;
+    }
+    __syncwarp();
+    return first;
+}
+
+// Java (int) cast of a double: truncate toward zero, saturate, NaN -> 0  (== cvt.rzi.s32.f64)
+__device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
+
+// ---------------------------------------------------------------------------------------
+// BattleSim  (O/BattleSim.java)
+// ---------------------------------------------------------------------------------------
+
+// One uniform against the (a,d) outcome table: first row with k <= floor(cdf_i * 2^53)
+// (== "r <= total", O/BattleSim.java:129-140); no row => no losses.
+// 32 rows are compared per step, one per lane.
+__device__ __forceinline__ void table_battle(const DevMap &dm, int a, int d, uint64_t k, int &al, int &dl)
+{
+    uint32_t meta = __ldg(dm.bt_meta + (a - 1) * ORX_TABLE_LIMIT + (d - 1));
+    const uint64_t *rows = dm.bt_rows + (meta >> 8);
+    int cnt = (int)(meta & 0xFFu);
+    uint64_t key = k << 11;
+    al = 0; dl = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        int i = base + lane_id();
+        uint64_t t = i < cnt ? __ldg(rows + i) : 0ull;
+        uint32_t hit = __ballot_sync(ORX_FULL, i < cnt && key <= t);
+        if (hit) {
+            uint32_t code = __shfl_sync(ORX_FULL, (uint32_t)t & 0xFFu, __ffs(hit) - 1);
+            int rem = (int)(code & 0x7Fu);
+            if (code & 0x80u) { al = a - rem; dl = d; } else { al = a; dl = d - rem; }
+            return;
+        }
+    }
+}
+
+// BattleSim.simulateIndividualBattle: attacker losses for one roll of pa v pd dice given k
+__device__ __forceinline__ int single_roll(const DevMap &dm, int pa, int pd, uint64_t k)
+{
+    int row = (pa - 1) * 2 + (pd - 1);
+    return k <= dm.single_thr[row][0] ? 0 : (k <= dm.single_thr[row][1] ? 1 : 2);
+}
+
+// BattleSim.simulateBattle (O/BattleSim.java:66-145)
+template <bool REPLAY>
+__device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY> &s, int attackers, int defenders,
+                                                int &alOut, int &dlOut)
+{
+    int attackerLosses = 0, defenderLosses = 0;
+    if (attackers > 500 && defenders > 500) {
+        int matched = java_d2i(__dmul_rn(0.922, (double)defenders));
+        if (matched > attackers) {
+            attackerLosses = attackers;
+            int variance = java_d2i(__dmul_rn(next_gaussian(s), __dsqrt_rn((double)attackers)));
+            double v = __dadd_rn((double)variance, __ddiv_rn((double)attackers, 0.922));
+            defenderLosses = java_d2i(fmin(v, (double)(defenders - 1)));
+        } else {
+            defenderLosses = defenders;
+            int variance = java_d2i(__dmul_rn(next_gaussian(s), __dsqrt_rn((double)defenders)));
+            int v = (int)((uint32_t)variance + (uint32_t)matched);
+            attackerLosses = v < attackers - 1 ? v : attackers - 1;
+        }
+    } else {
+        int ra = attackers, rd = defenders;
+        // single rolls while either side is above 100 (O/BattleSim.java:99-116), up to 32 rolls per
+        // step: every lane rolls with the next double of the block, and exactly the rolls the
+        // reference's loop would have played are consumed.
+        while ((ra > 100 || rd > 100) && ra > 0 && rd > 0 && !s.flags) {
+            int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
+            int avail = 0;
+            if (!REPLAY) {
+                if ((int32_t)(s.pos >> 7) != s.block) s.refill((int32_t)(s.pos >> 7));
+                avail = (int)(128u - (s.pos & 127u)) >> 1;
+                if (avail > 32) avail = 32;
+            }
+            if (avail == 0) {  // block boundary (or replay mode): one roll through the scalar path
+                int x = single_roll(dm, pa, pd, s.next_k53());
+                attackerLosses += x; defenderLosses += n - x; ra -= x; rd -= n - x;
+                continue;
+            }
+            int l = lane_id();
+            uint32_t base = (s.pos & 127u) + 2u * (uint32_t)l;
+            uint64_t k = 0;
+            if (l < avail) k = ((uint64_t)(s.buf[base] >> 6) << 27) + (uint64_t)(s.buf[base + 1] >> 5);
+            int x = single_roll(dm, pa, pd, k);
+            if (avail == 32 && ra >= 65 && rd >= 64 && (ra > 162 || rd > 162)) {
+                // no roll of this step can end the loop or change the dice: 3 v 2 throughout
+                int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 64 - la;
+                attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
+                s.pos += 64u;
+                continue;
+            }
+            uint32_t packed = (uint32_t)x | ((uint32_t)(n - x) << 16);  // (attacker, defender) losses
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t up = __shfl_up_sync(ORX_FULL, packed, o);
+                if (l >= o) packed += up;
+            }
+            int ra_l = ra - (int)(packed & 0xFFFFu), rd_l = rd - (int)(packed >> 16);
+            bool go_on = (ra_l > 100 || rd_l > 100) && ra_l > 0 && rd_l > 0 &&
+                         (ra_l < 3 ? ra_l : 3) == pa && (rd_l < 2 ? rd_l : 2) == pd;
+            uint32_t stop = __ballot_sync(ORX_FULL, !go_on || l >= avail - 1);
+            int last = __ffs(stop) - 1;  // rolls 0..last are played
+            uint32_t tot = __shfl_sync(ORX_FULL, packed, last);
+            int la = (int)(tot & 0xFFFFu), ld = (int)(tot >> 16);
+            attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
+            s.pos += 2u * (uint32_t)(last + 1);
+        }
+        if (ra != 0 && rd != 0 && !s.flags) {
+            if (ra < 0 || rd < 0 || ra > ORX_TABLE_LIMIT || rd > ORX_TABLE_LIMIT) {
+                s.flags |= ORX_FLAG_ERROR;
+            } else {
+                int al, dl;
+                table_battle(dm, ra, rd, s.next_k53(), al, dl);
+                attackerLosses += al; defenderLosses += dl;
+            }
+        }
+    }
+    alOut = attackerLosses; dlOut = defenderLosses;
+}
+
+// CardManager.getCardCashValue as integer closed forms (O/CardManager.java:283-341)
+__device__ __forceinline__ int card_cash_value(const DevMap &dm, int pos, uint32_t &flags)
+{
+    switch (dm.prog_family) {
+    case PROG_0: return 0;
+    case PROG_555: return 5;
+    case PROG_4466688: {  // (int)(ceil((sqrt(8*pos+9)-1)/2)*2): smallest k with (2k+1)^2 >= 8*pos+9
+        long long v = 8ll * pos + 9ll;
+        if (v <= 0) return 0;
+        long long k = (long long)((__dsqrt_rn((double)v) - 1.0) * 0.5);
+        while ((2 * k + 1) * (2 * k + 1) >= v && k > 0) k--;
+        while ((2 * k + 1) * (2 * k + 1) < v) k++;
+        return (int)(2 * k);
+    }
+    case PROG_456: return pos + 3;
+    case PROG_468: return (pos + 1) * 2;
+    case PROG_369: return pos * 3;
+    case PROG_46810: return pos <= 4 ? (pos + 1) * 2 : (pos - 2) * 5;
+    case PROG_51015: return pos * 5;
+    case PROG_4681015202510: return pos <= 4 ? (pos + 1) * 2 : (pos <= 7 ? (pos - 2) * 5 : 10);
+    case PROG_TABLE:
+        if (pos < 0 || pos >= ORX_CARD_VALUES) { flags |= ORX_FLAG_ERROR; return 0; }
+        return __ldg(dm.card_table + pos);
+    default: return 2;  // the catch block (O/CardManager.java:333-339)
+    }
+}
+
+}  // namespace orx

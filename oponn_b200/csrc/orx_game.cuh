@@ -1,0 +1,770 @@
+// orx_game.cuh -- one complete playout (setupState + simulate + getters) by one warp.
+//
+// Restates, in warp-uniform control flow with lane-parallel scans (O/ = /root/reference/src/com/mld46/oponn/):
+//   O/sim/boards/SimulationBoard.java:178-359 (setupState), :365-481 (simulate), :485-1015 (rules),
+//   :1076-1111 (income, next player);  O/sim/boards/ModellingBoard.java:21-47 (no observable effect for an
+//   all-SimRandom line-up);  O/sim/agents/SimRandom.java (whole: the playout policy);
+//   O/CardManager.java:240-346 (sim deck);  Card set semantics: declared assumption, see orx_state.h.
+//
+// Layout: territory t lives in lane t%32 of scan word t/32.  owner[] / armies[] / the ordered Java lists
+// (possibleAttackers, the hands, the sim deck) are byte / int arrays in this warp's shared-memory slice;
+// per-player counters (playerCountries, playerOutOnTurn, list sizes, initialArmiesLeftToPlace) are
+// lane-distributed registers (lane p <-> player p); everything else is a warp-uniform scalar.
+#pragma once
+
+#include "orx_device.cuh"
+
+namespace orx {
+
+struct RolloutArgs {
+    const uint8_t *leaves;        // n_leaves records, dm.leaf_stride apart
+    int32_t n_leaves, playouts_per_leaf;
+    unsigned long long total;     // n_leaves * playouts_per_leaf (replay: n_games)
+    unsigned long long seed, first_game;
+    OrxLeafResult *agg;           // [n_leaves] or null
+    OrxGameResult *games;         // [total] or null
+    unsigned long long *ticket;   // work counter (zeroed before launch)
+    const uint32_t *words;        // replay: explicit streams
+    uint32_t words_per_game;
+};
+
+template <int NWT, bool REPLAY>
+struct Game {
+    const DevMap &dm;
+    const uint8_t *sb;      // static map image in shared memory
+    int32_t *armies;
+    uint8_t *owner, *alist, *cards;
+    uint32_t *hdr;
+    Stream<REPLAY> s;
+    int lane;
+
+    // warp-uniform scalars (SimulationBoard.java:62-96)
+    int cp, phase, simTurn, remaining, placeable, cardpos, hasInvaded, playerTurns;
+    int attackState, attackingCC, defendingCC, attackingPlayer, defendingPlayer, attackUntilDead;
+    uint32_t termPos; bool termSet;
+    // lane-distributed: lane p = player p (list index P = the sim deck for ncard)
+    int pc, pot, ncard, ialp;
+
+    __device__ __forceinline__ Game(const DevMap &d) : dm(d) {}
+
+    __device__ __forceinline__ void fail() { s.flags |= ORX_FLAG_ERROR; }
+
+    // ---- static map accessors --------------------------------------------------------
+    __device__ __forceinline__ int adj(int t, int j) const { return sb[dm.adj_off + t * dm.degp + j]; }
+    __device__ __forceinline__ int deg(int t) const { return sb[dm.deg_off + t]; }
+    __device__ __forceinline__ uint32_t symbit(int card) const { return card == (int)ORX_CARD_WILD ? 8u : (uint32_t)sb[dm.sym_off + card]; }
+    __device__ __forceinline__ uint32_t nbr(int w, int t) const { return ((const uint32_t *)(sb + dm.nbr_off))[w * dm.NP + t]; }
+    __device__ __forceinline__ uint32_t contmask(int c, int w) const { return ((const uint32_t *)(sb + dm.cont_off))[c * NWT + w]; }
+
+    // ---- shared-memory helpers (one writer lane, fenced on both sides) ------------------
+    __device__ __forceinline__ void set_armies(int t, int v) { __syncwarp(); if (lane == 0) armies[t] = v; __syncwarp(); }
+    __device__ __forceinline__ void set_owner(int t, int v) { __syncwarp(); if (lane == 0) owner[t] = (uint8_t)v; __syncwarp(); }
+    template <typename T> __device__ __forceinline__ T from_lane(T v, int l) const { return __shfl_sync(ORX_FULL, v, l); }
+
+    // ---- ordered lists (java.util.List<Card>): list li < P is player li's hand, li == P the sim deck ----
+    __device__ __forceinline__ uint8_t *list(int li) const { return cards + li * dm.cap; }
+    __device__ __forceinline__ int list_len(int li) const { return from_lane(ncard, li); }
+    __device__ __forceinline__ void list_add(int li, int card)
+    {
+        int n = list_len(li);
+        if (n >= dm.cap) { fail(); return; }
+        __syncwarp();
+        if (lane == 0) list(li)[n] = (uint8_t)card;
+        if (lane == li) ncard++;
+        __syncwarp();
+    }
+    // remove(int index) on a byte list of length n held at p
+    __device__ __forceinline__ int bytes_remove_at(uint8_t *p, int n, int i)
+    {
+        int c = p[i];
+        for (int base = i; base < n - 1; base += 32) {
+            int idx = base + lane;
+            uint8_t v = idx < n - 1 ? p[idx + 1] : (uint8_t)0;
+            __syncwarp();
+            if (idx < n - 1) p[idx] = v;
+            __syncwarp();
+        }
+        return c;
+    }
+    __device__ __forceinline__ int list_remove_at(int li, int i)
+    {
+        int n = list_len(li);
+        int c = bytes_remove_at(list(li), n, i);
+        if (lane == li) ncard--;
+        return c;
+    }
+
+    // ---- board scans ------------------------------------------------------------------
+    // bitmask of the territories `player` owns, one word per scan word
+    __device__ __forceinline__ void owned_mask(int player, uint32_t (&m)[NWT]) const
+    {
+#pragma unroll
+        for (int w = 0; w < NWT; w++) m[w] = __ballot_sync(ORX_FULL, owner[w * 32 + lane] == player);
+    }
+    // owned territories with at least one out-neighbour not owned (SimRandom.java:68-82,250-262)
+    __device__ __forceinline__ void border_mask(const uint32_t (&mine)[NWT], bool need_two, uint32_t (&b)[NWT]) const
+    {
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int t = w * 32 + lane;
+            uint32_t enemy = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NWT; w2++) enemy |= nbr(w2, t) & ~mine[w2];
+            bool f = ((mine[w] >> lane) & 1u) && enemy != 0u && (!need_two || armies[t] > 1);
+            b[w] = __ballot_sync(ORX_FULL, f);
+        }
+    }
+    // territory index of the n-th set bit (code order) of a multi-word mask
+    __device__ __forceinline__ int nth_territory(const uint32_t (&m)[NWT], int n) const
+    {
+        int res = -1;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int c = __popc(m[w]);
+            if (res < 0 && n < c) res = w * 32 + nth_bit(m[w], n);
+            n -= c;
+        }
+        return res;
+    }
+    __device__ __forceinline__ int count_bits(const uint32_t (&m)[NWT]) const
+    {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) c += __popc(m[w]);
+        return c;
+    }
+
+    // ---- cards ------------------------------------------------------------------------
+    // DECLARED ASSUMPTION (Lux SDK Card.isASet not vendored, orx_state.h): wildcard, or all equal, or all distinct
+    static __device__ __forceinline__ bool is_set_bits(uint32_t m) { return (m & 8u) || __popc(m) != 2; }
+
+    // number of valid triples i<j<k of the current player's hand; when pick >= 0 also returns, in idx[],
+    // the pick-th one in lexicographic order (Card.containsASet / Card.getRandomSet)
+    __device__ __forceinline__ int scan_sets(int n, int pick, int idx[3])
+    {
+        const uint8_t *h = list(cp);
+        // symbol bits of the hand, staged in the (idle) attackers-list buffer
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) { int i = base + lane; if (i < n) alist[i] = (uint8_t)symbit(h[i]); }
+        __syncwarp();
+        int count = 0;
+        for (int i = 0; i < n - 2; i++) {
+            uint32_t si = alist[i];
+            for (int j = i + 1; j < n - 1; j++) {
+                uint32_t sij = si | alist[j];
+                for (int kb = j + 1; kb < n; kb += 32) {
+                    int k = kb + lane;
+                    bool ok = k < n && is_set_bits(sij | alist[k]);
+                    uint32_t m = __ballot_sync(ORX_FULL, ok);
+                    int c = __popc(m);
+                    if (pick >= count && pick < count + c) { idx[0] = i; idx[1] = j; idx[2] = kb + nth_bit(m, pick - count); }
+                    count += c;
+                }
+            }
+        }
+        return count;
+    }
+
+    // CardManager.simDeal (O/CardManager.java:250-263); returns -1 when the deck is legitimately empty
+    __device__ __forceinline__ int sim_deal()
+    {
+        int n = list_len(dm.P);
+        if (n == 0) { if (!dm.can_run_out) fail(); return -1; }
+        return list_remove_at(dm.P, s.next_int(n));
+    }
+
+    // SimulationBoard.cashCards (SimulationBoard.java:577-618) for hand positions i<j<k
+    __device__ __forceinline__ void cash_cards(const int idx[3])
+    {
+        const uint8_t *h = list(cp);
+        int c0 = h[idx[0]], c1 = h[idx[1]], c2 = h[idx[2]];
+        list_remove_at(cp, idx[2]); list_remove_at(cp, idx[1]); list_remove_at(cp, idx[0]);
+        list_add(dm.P, c0); list_add(dm.P, c1); list_add(dm.P, c2);  // CardManager.simCash :265-276
+        placeable += card_cash_value(dm, cardpos, s.flags);
+        cardpos++;
+        int cs[3] = { c0, c1, c2 };
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            if (cs[q] != (int)ORX_CARD_WILD && owner[cs[q]] == cp) set_armies(cs[q], armies[cs[q]] + 2);
+    }
+
+    // SimRandom.cardsPhase (SimRandom.java:36-49)
+    __device__ __forceinline__ void agent_cards_phase()
+    {
+        int n = list_len(cp);
+        if (n < 3) return;
+        int idx[3] = { 0, 0, 0 };
+        int count = scan_sets(n, -1, idx);
+        if (count == 0) return;
+        uint64_t k = s.next_k53();  // r < 0.5 <=> k < 2^52 ; r < 0.75 <=> k < 3 * 2^51
+        if ((n == 3 && k < (1ull << 52)) || (n == 4 && k < (3ull << 51)) || n >= 5) {
+            int pick = s.next_int(count);
+            scan_sets(n, pick, idx);
+            cash_cards(idx);
+        }
+    }
+
+    // SimulationBoard.tearDownCardsPhase (:620-638)
+    __device__ __forceinline__ void tear_down_cards_phase()
+    {
+        for (;;) {
+            int n = list_len(cp);
+            if (n <= 4 || s.flags) break;
+            int idx[3] = { 0, 0, 0 };
+            int count = scan_sets(n, -1, idx);
+            if (count == 0) { fail(); break; }
+            int pick = s.next_int(count);
+            scan_sets(n, pick, idx);
+            cash_cards(idx);
+        }
+        phase = ORX_PHASE_PLACEMENT;
+    }
+
+    // ---- placement --------------------------------------------------------------------
+    // SimRandom.place (SimRandom.java:247-277) + SimulationBoard.placeArmies (:647-684)
+    __device__ __forceinline__ void agent_place(int n_armies)
+    {
+        uint32_t mine[NWT], cand[NWT];
+        owned_mask(cp, mine);
+        border_mask(mine, false, cand);
+        int n = count_bits(cand);
+        while (n_armies > 0 && !s.flags) {
+            int k = 1 + s.next_int(n_armies);
+            int i = s.next_int(n);
+            if (s.flags) return;
+            int t = nth_territory(cand, i);
+            set_armies(t, armies[t] + k);
+            placeable -= k;
+            if (phase == ORX_PHASE_INITIAL_PLACEMENT && lane == cp) ialp -= k;
+            n_armies -= k;
+        }
+    }
+
+    // SimulationBoard.getPlayerIncome(currentPlayer) (:1076-1090, quirk 3 is moot: player == currentPlayer)
+    __device__ __forceinline__ int player_income()
+    {
+        int mycount = from_lane(pc, cp);
+        if (mycount == 0) return 0;
+        uint32_t mine[NWT];
+        owned_mask(cp, mine);
+        int income = mycount / 3; if (income < 3) income = 3;
+        int bonus = 0;
+        if (lane < dm.C) {
+            uint32_t missing = 0;
+#pragma unroll
+            for (int w = 0; w < NWT; w++) missing |= contmask(lane, w) & ~mine[w];
+            if (missing == 0u) bonus = current_bonus(lane);
+        }
+        return (int)((uint32_t)income + __reduce_add_sync(ORX_FULL, (unsigned)bonus));
+    }
+
+    // currentContinentBonuses[c] (recalculateContinentBonuses :956-963), rows precomputed on the host
+    __device__ __forceinline__ int current_bonus(int c) const
+    {
+        if (dm.cont_inc == 0) return ((const int32_t *)(sb + dm.bonus_off))[c];
+        int e = (int)hdr[WH_SIM_START] + simTurn - 1; if (e < 0) e = 0;
+        return __ldg(dm.bonus_table + e * dm.C + c);
+    }
+    __device__ __forceinline__ void recalculate_bonuses()
+    {
+        int e = (int)hdr[WH_SIM_START] + simTurn - 1;
+        if (dm.cont_inc != 0 && e >= ORX_BONUS_ROUNDS) fail();  // engine table limit
+    }
+
+    // ---- attack -----------------------------------------------------------------------
+    // SimulationBoard.playerDefeated (:843-867)
+    __device__ __forceinline__ void player_defeated(int player, int conquerer)
+    {
+        remaining--;
+        if (lane == player) pot = simTurn;
+        int dst = dm.transfer_cards ? conquerer : dm.P;  // hand -> conqueror, or simReturnToDeck
+        if (dst < 0) { fail(); return; }
+        if (dst != player) {
+            int nsrc = list_len(player), ndst = list_len(dst);
+            if (ndst + nsrc > dm.cap) { fail(); return; }
+            const uint8_t *src = list(player); uint8_t *d = list(dst);
+            __syncwarp();
+            for (int base = 0; base < nsrc; base += 32) { int i = base + lane; if (i < nsrc) d[ndst + i] = src[i]; }
+            __syncwarp();
+            if (lane == dst) ncard += nsrc;
+            if (lane == player) ncard = 0;  // the reference leaves a stale copy that nothing reads
+        }
+        if (remaining == 1) {
+            if (lane == cp) pot = -1;
+            if (!termSet) { termSet = true; termPos = s.pos; }
+        }
+    }
+
+    // SimulationBoard.executeAttack (:758-780): losses for the armies on attackingCC / defendingCC
+    __device__ __forceinline__ void execute_attack(int A, int D, int &al, int &dl)
+    {
+        int a = armies[A] - 1, d = armies[D];
+        if (attackUntilDead) {
+            simulate_battle(dm, s, a, d, al, dl);
+        } else {
+            int pa = a < 3 ? a : 3, pd = d < 2 ? d : 2;
+            if (pa < 1 || pd < 1) { fail(); al = dl = 0; return; }
+            al = single_roll(dm, pa, pd, s.next_k53());
+            dl = (pa < pd ? pa : pd) - al;
+        }
+    }
+
+    // SimRandom.moveArmiesIn (SimRandom.java:144-155) + executeInvasion (:814-825)
+    __device__ __forceinline__ void invade(int A, int D)
+    {
+        int aArm = armies[A];
+        int available = aArm - 1;
+        if (available == 0) { fail(); return; }
+        int mn = available < 3 ? available : 3;
+        int req = mn + (mn == available ? 0 : s.next_int(available - mn));
+        int lo = aArm - 1 < 3 ? aArm - 1 : 3, hi = aArm - 1;
+        int inv = req > lo ? req : lo; if (inv > hi) inv = hi;
+        __syncwarp();
+        if (lane == 0) { armies[D] = inv; armies[A] = aArm - inv; }
+        __syncwarp();
+    }
+
+    // finishInvasion (:827-841)
+    __device__ __forceinline__ void finish_invasion()
+    {
+        if (defendingPlayer < 0 || defendingPlayer >= dm.P) { fail(); return; }
+        if (from_lane(pc, defendingPlayer) == 0) player_defeated(defendingPlayer, attackingPlayer);
+        hasInvaded = 1;
+        attackState = ORX_ATTACK_START;
+        attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
+    }
+
+    // SimRandom.attackPhase (SimRandom.java:58-141) with SimulationBoard.attack (:713-744) inlined
+    __device__ __forceinline__ void agent_attack_phase()
+    {
+        uint32_t mine[NWT], att[NWT];
+        owned_mask(cp, mine);
+        border_mask(mine, true, att);
+        // possibleAttackers: code order
+        int nAtt = 0;
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            if ((att[w] >> lane) & 1u) alist[nAtt + __popc(att[w] & lanemask_lt())] = (uint8_t)(w * 32 + lane);
+            nAtt += __popc(att[w]);
+        }
+        __syncwarp();
+        uint32_t guard = 0;
+        while (nAtt > 0 && !s.flags) {
+            if (++guard > (1u << 24)) { fail(); break; }
+            int ai = s.next_int(nAtt);
+            int A = alist[ai];
+            // possibleDefenders: non-owned out-neighbours in getAdjoiningList() order
+            int dg = deg(A);
+            int nb = lane < dg ? adj(A, lane) : 0;
+            bool enemy = lane < dg && owner[nb] != cp;
+            uint32_t dmask = __ballot_sync(ORX_FULL, enemy);
+            int nDef = __popc(dmask);
+            if (nDef == 0) { bytes_remove_at(alist, nAtt, ai); nAtt--; continue; }
+            int D = from_lane(nb, nth_bit(dmask, s.next_int(nDef)));
+            // SimulationBoard.attack: setupAttack, executeAttack, finishAttack
+            attackUntilDead = 1;
+            int al, dl;
+            execute_attack(A, D, al, dl);
+            if (s.flags) return;
+            int aArm = armies[A] - al, dArm = armies[D] - dl;
+            __syncwarp();
+            if (lane == 0) { armies[A] = aArm; armies[D] = dArm; }
+            __syncwarp();
+            if (dArm == 0) {
+                // setupInvasion (:797-812)
+                int dp = owner[D];
+                if (lane == cp) pc++;
+                if (lane == dp) pc--;
+                set_owner(D, cp);
+                attackingPlayer = cp; defendingPlayer = dp;
+                invade(A, D);
+                if (s.flags) return;
+                finish_invasion();
+                if (s.flags) return;
+                // result == DEFENDERS_DESTROYED (SimRandom.java:127-137)
+                if (armies[A] == 1) { bytes_remove_at(alist, nAtt, ai); nAtt--; }
+                if (armies[D] > 1) {
+                    if (nAtt >= dm.cap) { fail(); return; }
+                    __syncwarp(); if (lane == 0) alist[nAtt] = (uint8_t)D; __syncwarp();
+                    nAtt++;
+                }
+            } else {
+                attackState = ORX_ATTACK_START;
+                if (aArm == 1) { bytes_remove_at(alist, nAtt, ai); nAtt--; }  // ATTACKERS_DESTROYED
+            }
+        }
+    }
+
+    // tearDownAttackPhase (:884-896)
+    __device__ __forceinline__ void tear_down_attack_phase()
+    {
+        if (hasInvaded && dm.use_cards) {
+            int card = sim_deal();
+            if (card >= 0) list_add(cp, card);
+        }
+        phase = ORX_PHASE_FORTIFICATION;
+    }
+
+    // ---- fortification / turn advance -------------------------------------------------
+    // checkForOverflow (:984-1015)
+    __device__ __forceinline__ void check_for_overflow()
+    {
+        int mysum = 0;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N) mysum += armies[t]; }
+        int total = (int)__reduce_add_sync(ORX_FULL, (unsigned)mysum);
+        if (total <= 100000) return;
+        int maxArmies = 0, maxPlayer = -1;
+        for (int p = 0; p < dm.P; p++) {
+            int ps = 0;
+#pragma unroll
+            for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N && owner[t] == p) ps += armies[t]; }
+            int tot = (int)__reduce_add_sync(ORX_FULL, (unsigned)ps);
+            if (tot > maxArmies) { maxPlayer = p; maxArmies = tot; }
+        }
+        for (int p = 0; p < dm.P; p++)
+            if (from_lane(pc, p) > 0 && p != maxPlayer) { player_defeated(p, maxPlayer); if (s.flags) return; }
+    }
+
+    // tearDownFortificationPhase (:965-982) with getNextPlayer (:1102-1111)
+    __device__ __forceinline__ void tear_down_fortification_phase()
+    {
+        uint32_t alive = __ballot_sync(ORX_FULL, lane < dm.P && pc > 0);
+        if (alive == 0u) { fail(); return; }  // the reference would spin forever
+        uint32_t above = alive & ~((2u << cp) - 1u);
+        int np = above ? __ffs(above) - 1 : __ffs(alive) - 1;
+        if (np < cp) { simTurn++; recalculate_bonuses(); }
+        cp = np;
+        phase = ORX_PHASE_CARDS;
+        if (!s.flags) check_for_overflow();
+        playerTurns++;
+    }
+
+    // ---- pre-game phases (SimulationBoard.java:485-568, SimRandom.java:16-27) ----------
+    __device__ __forceinline__ void setup_initial_placement_phase()
+    {
+        int a = from_lane(ialp, cp);
+        placeable = a == 5 ? 5 : (a < 4 ? a : 4);
+    }
+    __device__ __forceinline__ void tear_down_country_selection_phase()
+    {
+        if ((int)hdr[WH_REM_COUNTRIES] == 0) { phase = ORX_PHASE_INITIAL_PLACEMENT; cp = 0; }
+    }
+    __device__ __forceinline__ void select_country()
+    {
+        uint32_t free_[NWT];
+        owned_mask((int)ORX_OWNER_NONE, free_);
+        int n = count_bits(free_);
+        int i = s.next_int(n);  // nextInt(0) throws
+        if (s.flags) return;
+        int cc = nth_territory(free_, i);
+        set_owner(cc, cp);
+        if (lane == cp) { pc++; ialp--; }
+        __syncwarp();
+        if (lane == 0) hdr[WH_REM_COUNTRIES] -= 1u;
+        __syncwarp();
+        cp = (cp + 1) % dm.P;
+    }
+    __device__ __forceinline__ void tear_down_initial_placement_phase()
+    {
+        // next player (cyclic, excluding the current one) who still has armies to place
+        uint32_t todo = __ballot_sync(ORX_FULL, lane < dm.P && ialp != 0) & ~(1u << cp);
+        if (todo == 0u) {
+            cp = 0; phase = ORX_PHASE_CARDS; simTurn++;
+        } else {
+            uint32_t above = todo & ~((2u << cp) - 1u);
+            cp = above ? __ffs(above) - 1 : __ffs(todo) - 1;
+        }
+        playerTurns++;
+    }
+
+    __device__ __forceinline__ void step_limit_hit()
+    {
+        if (playerTurns >= dm.max_turns) s.flags |= ORX_FLAG_STEP_LIMIT;
+    }
+
+    // ---- setupState (:178-359) from a packed leaf record --------------------------------
+    __device__ __forceinline__ void setup_state(const uint8_t *leaf)
+    {
+        const uint32_t *hw = (const uint32_t *)leaf;  // header words (orx_state.h OrxLeafHeader)
+        uint32_t h2 = __ldg(hw + 2), h3 = __ldg(hw + 3), h4 = __ldg(hw + 4), h5 = __ldg(hw + 5);
+        int turn_count = (int)__ldg(hw + 0);
+        int h_placeable = (int)__ldg(hw + 1);
+        int h_acc = (int)(int16_t)(h2 & 0xFFFFu), h_dcc = (int)(int16_t)(h2 >> 16);
+        int h_cardpos = (int)(int16_t)(h3 & 0xFFFFu);
+        int h_cp = (int)(int8_t)((h3 >> 16) & 0xFFu), h_phase = (int)(int8_t)(h3 >> 24);
+        int h_astate = (int)(int8_t)(h4 & 0xFFu), h_inv = (int)(int8_t)((h4 >> 8) & 0xFFu);
+        int h_dp = (int)(int8_t)((h4 >> 16) & 0xFFu), h_aud = (int)(int8_t)(h4 >> 24);
+        int n_hand = (int)(h5 & 0xFFu), n_deck = (int)((h5 >> 8) & 0xFFu);
+        const int N = dm.N, P = dm.P;
+
+        // engine-level record validation (orx_state.h "Leaf validity"): the same rules as the oracle
+        bool bad = h_cp < 0 || h_cp >= P || h_phase < 0 || h_phase > ORX_PHASE_FORTIFICATION ||
+                   h_astate < 0 || h_astate > ORX_ATTACK_PLACE || h_acc < -1 || h_acc >= N || h_dcc < -1 || h_dcc >= N ||
+                   h_dp < -1 || h_dp >= P || h_cardpos < 0 || n_hand + n_deck > N + 2 ||
+                   h_placeable < -ORX_MAX_ARMIES || h_placeable > ORX_MAX_ARMIES;
+
+        // setupCountries (:192-203)
+        __syncwarp();
+        bool badt = false;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int t = w * 32 + lane;
+            int o = 0xFE, a = 0;
+            if (t < N) {
+                o = __ldg(leaf + dm.off_owner + t);
+                a = __ldg((const int32_t *)(leaf + dm.off_armies) + t);
+                if (!(o < P || (o == (int)ORX_OWNER_NONE && h_phase == ORX_PHASE_COUNTRY_SELECTION))) badt = true;
+                if (a < 1 || a > ORX_MAX_ARMIES) badt = true;
+            }
+            owner[t] = (uint8_t)o; armies[t] = a;
+        }
+        // cards: hand then deck (CardManager.simReset :240-248)
+        const uint8_t *lc = leaf + dm.off_cards;
+        for (int base = 0; base < n_hand + n_deck && base < N + 2; base += 32) {
+            int i = base + lane;
+            if (i < n_hand + n_deck && i < N + 2) {
+                int c = __ldg(lc + i);
+                if (!(c < N || c == (int)ORX_CARD_WILD)) badt = true;
+                if (!bad) { if (i < n_hand) list(h_cp)[i] = (uint8_t)c; else list(P)[i - n_hand] = (uint8_t)c; }
+            }
+        }
+        int my_ncards = lane < P ? (int)__ldg(leaf + dm.off_ncards + lane) : 0;
+        __syncwarp();
+        if (bad || __any_sync(ORX_FULL, badt)) { fail(); return; }
+
+        cp = h_cp; phase = h_phase; simTurn = 0; cardpos = h_cardpos;
+        placeable = 0; hasInvaded = 0; playerTurns = 0;
+        attackState = ORX_ATTACK_START; attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
+        attackUntilDead = h_aud != 0;
+        termSet = false; termPos = 0;
+        pot = 0; ialp = 0;
+        ncard = lane == cp ? n_hand : (lane == P ? n_deck : 0);
+        if (lane == 0) { hdr[WH_SIM_START] = (uint32_t)turn_count; hdr[WH_REM_COUNTRIES] = 0u; }
+        __syncwarp();
+
+        // setupCardState (:205-227): hidden hands are dealt at random, in player order
+        for (int p = 0; p < P; p++) {
+            if (p == cp) continue;
+            int want = from_lane(my_ncards, p);
+            for (int j = 0; j < want; j++) {
+                int card = sim_deal();
+                if (card < 0) { fail(); return; }  // the reference would store null and fail later
+                if (s.flags) return;
+                list_add(p, card);
+            }
+        }
+
+        // setupGeneralGameState (:229-276)
+        {
+            int cnt = 0;
+            for (int p = 0; p < P; p++) {
+                uint32_t m[NWT];
+                owned_mask(p, m);
+                int c = count_bits(m);
+                if (lane == p) cnt = c;
+            }
+            pc = cnt;
+            remaining = phase == ORX_PHASE_COUNTRY_SELECTION ? P : __popc(__ballot_sync(ORX_FULL, lane < P && pc > 0));
+        }
+
+        // setupPhaseGameState (:278-359)
+        int start = dm.start_armies + (lane > 1 ? lane : 0);  // calculateStartingArmies (:518-533)
+        switch (phase) {
+        case ORX_PHASE_COUNTRY_SELECTION: {
+            uint32_t free_[NWT];
+            owned_mask((int)ORX_OWNER_NONE, free_);
+            ialp = start - pc;
+            __syncwarp();
+            if (lane == 0) hdr[WH_REM_COUNTRIES] = (uint32_t)count_bits(free_);
+            __syncwarp();
+            break;
+        }
+        case ORX_PHASE_INITIAL_PLACEMENT: {
+            int mine_total = 0;
+            for (int p = 0; p < P; p++) {
+                int ps = 0;
+#pragma unroll
+                for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (owner[t] == p) ps += armies[t]; }
+                int tot = (int)__reduce_add_sync(ORX_FULL, (unsigned)ps);
+                if (lane == p) mine_total = tot;
+            }
+            ialp = start - mine_total;
+            placeable = h_placeable;
+            break;
+        }
+        case ORX_PHASE_CARDS:
+        case ORX_PHASE_PLACEMENT:
+            placeable = h_placeable;
+            break;
+        case ORX_PHASE_ATTACK:
+            hasInvaded = h_inv != 0;
+            attackState = h_astate;
+            attackingCC = h_acc; defendingCC = h_dcc;
+            if (attackingCC != -1) { attackingPlayer = owner[attackingCC]; defendingPlayer = h_dp; }
+            if (h_astate == ORX_ATTACK_INVADE) {
+                if (defendingPlayer < 0 || defendingPlayer >= P) { fail(); return; }
+                if (from_lane(pc, defendingPlayer) == 0) remaining++;
+            } else if (h_astate == ORX_ATTACK_CASH || h_astate == ORX_ATTACK_PLACE) {
+                placeable = h_placeable;
+            }
+            break;
+        default:  // FORTIFICATION
+            break;
+        }
+        recalculate_bonuses();
+    }
+
+    // ---- simulate (:365-481): the catch-up pass is the first trip through the same switch ----
+    __device__ __forceinline__ void simulate()
+    {
+        bool first = true;
+        for (;;) {
+            if (s.flags) break;
+            if (!first && remaining <= 1) break;
+            switch (phase) {
+            case ORX_PHASE_COUNTRY_SELECTION:
+                if (!first) select_country();
+                if (!s.flags) tear_down_country_selection_phase();
+                break;
+            case ORX_PHASE_INITIAL_PLACEMENT:
+                if (!first) setup_initial_placement_phase();
+                agent_place(placeable);
+                tear_down_initial_placement_phase();
+                if (!first) step_limit_hit();
+                break;
+            case ORX_PHASE_CARDS:
+                if (!first) placeable = 0;  // setupCardsPhase (:572-575)
+                agent_cards_phase();
+                tear_down_cards_phase();
+                break;
+            case ORX_PHASE_PLACEMENT:
+                if (!first) placeable = (int)((uint32_t)placeable + (uint32_t)player_income());  // setupPlacementPhase
+                agent_place(placeable);
+                phase = ORX_PHASE_ATTACK;  // tearDownPlacementPhase (:686-694)
+                break;
+            case ORX_PHASE_ATTACK:
+                if (!first) {
+                    hasInvaded = 0;  // setupAttackPhase (:698-707)
+                    attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
+                    attackState = ORX_ATTACK_START;
+                } else {
+                    if (attackState == ORX_ATTACK_EXECUTE) {
+                        if (attackingCC < 0 || defendingCC < 0) { fail(); break; }
+                        int al, dl;
+                        execute_attack(attackingCC, defendingCC, al, dl);
+                        if (s.flags) break;
+                        int aArm = armies[attackingCC] - al, dArm = armies[defendingCC] - dl;  // finishAttack
+                        set_armies(attackingCC, aArm); set_armies(defendingCC, dArm);
+                        attackState = armies[defendingCC] == 0 ? ORX_ATTACK_INVADE : ORX_ATTACK_START;
+                    }
+                    if (attackState == ORX_ATTACK_INVADE) {
+                        // no setupInvasion() on this path: SURVEY 8.1 quirk 1
+                        if (attackingCC < 0 || defendingCC < 0) { fail(); break; }
+                        invade(attackingCC, defendingCC);
+                        if (s.flags) break;
+                        finish_invasion();
+                        if (s.flags) break;
+                    }
+                    if (attackState == ORX_ATTACK_CASH) {  // executeAttackCash (:869-876)
+                        placeable = 0;
+                        agent_cards_phase();
+                        attackState = ORX_ATTACK_PLACE;
+                        if (s.flags) break;
+                    }
+                    if (attackState == ORX_ATTACK_PLACE) {  // executeAttackPlacement (:878-882)
+                        agent_place(placeable);
+                        attackState = ORX_ATTACK_START;
+                        if (s.flags) break;
+                    }
+                }
+                agent_attack_phase();
+                if (!s.flags) tear_down_attack_phase();
+                break;
+            default:  // FORTIFICATION: SimRandom.fortifyPhase is a no-op (SimRandom.java:158-160)
+                tear_down_fortification_phase();
+                if (!first) step_limit_hit();
+                break;
+            }
+            first = false;
+        }
+    }
+
+    // ---- result record (SimulationBoard.java:1031-1044 + the parity pins of orx_state.h) ----
+    __device__ __forceinline__ void write_result(OrxGameResult *out, OrxLeafResult *agg)
+    {
+        uint32_t flags = s.flags;
+        bool dead = (flags & (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END)) != 0u;
+        if (dead) flags &= (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END);
+        uint32_t hsum = 0;
+        if (!dead) {
+#pragma unroll
+            for (int w = 0; w < NWT; w++) {
+                int t = w * 32 + lane;
+                if (t < dm.N) hsum += orx_mix((uint32_t)t, (uint32_t)owner[t], (uint32_t)armies[t]);
+            }
+            hsum = __reduce_add_sync(ORX_FULL, hsum);
+        }
+        int my_pot = (!dead && lane < dm.P) ? pot : 0;
+        int turns = dead ? 0 : simTurn;
+        uint32_t spos = dead ? 0u : (termSet ? termPos : s.pos);
+        if (out) {
+            uint32_t v = lane < ORX_MAX_PLAYERS ? (uint32_t)my_pot
+                       : lane == 8 ? (uint32_t)turns : lane == 9 ? flags : lane == 10 ? spos : hsum;
+            if (lane < 12) ((uint32_t *)out)[lane] = v;
+        }
+        if (agg) {
+            unsigned long long *a = (unsigned long long *)agg;  // n, len_sum, wins[8], win_len_sum[8], flagged
+            if (lane < ORX_MAX_PLAYERS && my_pot == -1) {
+                atomicAdd(a + 2 + lane, 1ull);
+                atomicAdd(a + 10 + lane, (unsigned long long)(long long)turns);
+            }
+            if (lane == 8) { atomicAdd(a + 0, 1ull); atomicAdd(a + 1, (unsigned long long)(long long)turns); }
+            if (lane == 9 && flags) atomicAdd(a + 18, 1ull);
+        }
+    }
+};
+
+// The rollout kernel: persistent warps pull game indices from a ticket counter.
+template <int NWT, bool REPLAY>
+__global__ void __launch_bounds__(ORX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ RolloutArgs ar)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    // stage the static map image
+    {
+        const uint4 *src = (const uint4 *)dm.blob; uint4 *dst = (uint4 *)smem;
+        for (int i = threadIdx.x; i < dm.blob_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5;
+    uint8_t *slice = smem + dm.blob_bytes + wid * dm.w_bytes;
+
+    Game<NWT, REPLAY> g(dm);
+    g.sb = smem;
+    g.lane = lane_id();
+    g.hdr = (uint32_t *)slice;
+    g.armies = (int32_t *)(slice + dm.w_armies);
+    g.owner = slice + dm.w_owner;
+    g.alist = slice + dm.w_alist;
+    g.cards = slice + dm.w_cards;
+    uint32_t *rng = (uint32_t *)(slice + dm.w_rng);
+
+    for (;;) {
+        unsigned long long idx = 0;
+        if (g.lane == 0) idx = atomicAdd(ar.ticket, 1ull);
+        idx = __shfl_sync(ORX_FULL, idx, 0);
+        if (idx >= ar.total) break;
+        unsigned long long leaf_i = REPLAY ? idx : idx / (unsigned long long)ar.playouts_per_leaf;
+        const uint8_t *leaf = ar.leaves + leaf_i * (unsigned long long)dm.leaf_stride;
+        g.s.init(rng, g.hdr, ar.seed, ar.first_game + idx,
+                 REPLAY ? ar.words + idx * (unsigned long long)ar.words_per_game : nullptr, ar.words_per_game);
+        g.simTurn = 0; g.pot = 0; g.termSet = false; g.termPos = 0;
+        g.setup_state(leaf);
+        if (!g.s.flags) g.simulate();
+        g.write_result(ar.games ? ar.games + idx : nullptr, ar.agg ? ar.agg + leaf_i : nullptr);
+        __syncwarp();
+    }
+}
+
+}  // namespace orx

@@ -1,0 +1,91 @@
+"""Regenerates the committed fixtures under tests/golden/ with the CPU oracle (oracle/oponn_oracle.c).
+
+    python tests/golden/make_golden.py
+
+The Java reference cannot run in this image (no JDK; Lux SDK not vendored), so game-level goldens are
+outputs of the oracle restatement, frozen here so that (a) the oracle itself is regression-pinned and
+(b) the CUDA engine is compared against bytes that do not depend on the oracle being rebuilt.
+
+Files written:
+  classic42_mid_s1.leaf    one packed leaf record (SURVEY.md 8d recipe, state seed 1)
+  classic42_mid_64.leaves  64 packed records, state seeds 1..64 (distinct mid-game positions)
+  synth200_mid_s1.leaf     the large-map analogue (BASELINE.json config 4)
+  golden_games.npz         per-game result records for those leaves under run seed 20261019
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from oponn_b200.maps import classic42, synth200  # noqa: E402
+from oponn_b200.state import PHASE_INITIAL_PLACEMENT, BoardState, Rules  # noqa: E402
+from oracle.pyoracle import Oracle  # noqa: E402
+
+RUN_SEED = 20261019
+
+
+def new_game_leaf(m, state_seed: int) -> np.ndarray:
+    """SimulationBoard.setupNewGame analogue (SimulationBoard.java:141-176): shuffled territories dealt
+    round-robin, one army each, INITIAL_PLACEMENT about to start with player 0."""
+    rng = np.random.default_rng(state_seed)
+    perm = rng.permutation(m.n_territories)
+    owner = [0] * m.n_territories
+    for i, cc in enumerate(perm):
+        owner[int(cc)] = i % m.n_players
+    bs = BoardState(owner=owner, armies=[1] * m.n_territories, currentPlayer=0, currentPhase=PHASE_INITIAL_PLACEMENT,
+                    turnCount=0, playerNumberOfCards=[0] * m.n_players, numberOfPlaceableArmies=4, cardProgressionPos=1)
+    return bs.pack(m)
+
+
+def mid_game_leaf(o: Oracle, m, state_seed: int, rounds: int = 3):
+    """Initial placement + `rounds` full rounds under SimRandom, snapshot at the start of a CARDS phase with
+    every player alive; the seed is bumped by 1000 until that holds (returns the seed used)."""
+    seed = state_seed
+    while True:
+        alive, leaf = o.advance_to_leaf(new_game_leaf(m, seed), seed, 0, 1 + rounds)
+        if alive == m.n_players:
+            return seed, leaf
+        seed += 1000
+
+
+def main():
+    out = {}
+    m, r = classic42(6), Rules()
+    o = Oracle(m, r)
+    used, leaf = mid_game_leaf(o, m, 1)
+    leaf.tofile(os.path.join(HERE, "classic42_mid_s1.leaf"))
+    print("classic42_mid_s1: state seed used", used)
+    _, games = o.rollout_batch(leaf[None, :], 512, RUN_SEED, per_game=True, threads=8)
+    out["classic42_mid_s1"] = games
+    leaves = []
+    seeds = []
+    for s in range(1, 65):
+        u, lf = mid_game_leaf(o, m, s)
+        leaves.append(lf); seeds.append(u)
+    leaves = np.stack(leaves)
+    leaves.tofile(os.path.join(HERE, "classic42_mid_64.leaves"))
+    _, games = o.rollout_batch(leaves, 4, RUN_SEED, per_game=True, threads=8)
+    out["classic42_mid_64"] = games
+    out["classic42_mid_64_seeds"] = np.array(seeds)
+    o.close()
+
+    m2, r2 = synth200(), Rules(max_player_turns=4096)
+    o2 = Oracle(m2, r2)
+    used, leaf2 = mid_game_leaf(o2, m2, 1)
+    leaf2.tofile(os.path.join(HERE, "synth200_mid_s1.leaf"))
+    print("synth200_mid_s1: state seed used", used)
+    _, games = o2.rollout_batch(leaf2[None, :], 64, RUN_SEED, per_game=True, threads=8)
+    out["synth200_mid_s1"] = games
+    o2.close()
+    np.savez_compressed(os.path.join(HERE, "golden_games.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape, v.dtype.names if v.dtype.names else "")
+
+
+if __name__ == "__main__":
+    main()
