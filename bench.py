@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: complete Risk playouts/sec to a terminal game (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--playouts P]
+
+A "step" is one move's worth of rollouts: P (default 1,048,576 -- BASELINE.json configs[1]) complete
+random playouts from the frozen mid-game leaf ``classic42_mid_s1`` on each GPU (weak scaling), followed,
+for N > 1, by the one exchange the path has: an NCCL all-reduce of the per-leaf win/length sums
+(root-parallel merge, once per move).  One JSON line on stdout; see DESIGN.md "Measurement".
+
+``--impl reference`` times the CPU restatement of the Java simulator (oracle/, all host threads) on a
+bounded sample of the same workload: the Java reference itself cannot run here (no JDK, no Lux SDK).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RUN_SEED = 20261019
+METRIC = "risk_playouts_per_sec_to_terminal"
+UNIT = "playouts/s"
+WORKLOAD = "classic42 (42 territories, 6 players, cards on, transfer on), leaf classic42_mid_s1, all-SimRandom playouts"
+
+
+def load_leaf() -> np.ndarray:
+    return np.fromfile(os.path.join(ROOT, "tests", "golden", "classic42_mid_s1.leaf"), dtype=np.uint8)
+
+
+def load_workload() -> dict:
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "workload_classic42_mid_s1.json")))
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p)); d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md "clocks line")
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc = device, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, smax, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle restatement on host cores (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_rollouts(playouts: int, threads: int, steps: int = 1, warmup: int = 0):
+    from oponn_b200.maps import classic42
+    from oponn_b200.state import Rules
+    from oracle.pyoracle import Oracle
+    o = Oracle(classic42(6), Rules())
+    leaf = load_leaf()[None, :]
+    for w in range(warmup):
+        o.rollout_batch(leaf, playouts, RUN_SEED, first_game=w * playouts, per_game=False, threads=threads)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        o.rollout_batch(leaf, playouts, RUN_SEED, first_game=(warmup + s) * playouts, per_game=False, threads=threads)
+    dt = time.perf_counter() - t0
+    o.close()
+    return dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = 64 * cores  # playouts per step: a bounded sample of the 1M-playout move
+    dt = cpu_rollouts(sample, cores, steps=args.steps, warmup=args.warmup)
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "playouts_per_step": sample, "note": "bounded sample of the 1,048,576-playout move"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} playouts/step x {args.steps} steps, oracle/oponn_oracle.c -O2, {cores} threads "
+                                   "(C restatement of the Java simulator; JVM and Lux SDK unavailable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from oponn_b200.engine import RolloutEngine
+    from oponn_b200.maps import classic42
+    from oponn_b200.state import LEAF_RESULT_DTYPE, Rules
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rollout engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    P = args.playouts
+    eng = RolloutEngine(classic42(6), Rules(), device=local)
+    leaf = load_leaf()
+    stride = eng.layout.stride
+    leaf_dev = torch.from_numpy(leaf.copy()).to(dev)
+    agg_words = LEAF_RESULT_DTYPE.itemsize // 8
+    agg_dev = torch.zeros(agg_words, dtype=torch.int64, device=dev)
+    leaf_pin = torch.from_numpy(leaf.copy()).pin_memory()
+    agg_pin = torch.zeros(agg_words, dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_ms = []
+
+    def step_device(i: int):
+        """inputs resident in HBM; results stay on the device; N > 1: all-reduce of the per-leaf sums"""
+        flush.zero_()
+        torch.cuda.synchronize()
+        first = (i * world + rank) * P
+        eng.rollout_batch_device(leaf_dev.data_ptr(), 1, P, RUN_SEED, first, agg_dev.data_ptr())
+        eng.sync()
+        kernel_ms.append(eng.last_kernel_ms)
+        if world > 1:
+            dist.all_reduce(agg_dev)
+            torch.cuda.synchronize()
+
+    def step_e2e(i: int):
+        """the reference-facing call: HOST leaf in, HOST aggregates out, copies inside the timed region"""
+        first = (i * world + rank) * P
+        eng._ck(eng._L.orx_rollout_batch(eng._h, leaf_pin.data_ptr(), 1, P, RUN_SEED, first, agg_pin.data_ptr(), None))
+        if world > 1:
+            t = agg_pin.to(dev, non_blocking=True)
+            dist.all_reduce(t)
+            agg_pin.copy_(t)
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, base):
+        for w in range(warmup):
+            fn(base + w)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            fn(base + warmup + s)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    sampler = ClockSampler(local)
+    launches0 = eng.kernel_launches
+    if rank == 0:
+        sampler.start()
+    kernel_ms.clear()
+    dt = timed(step_device, args.steps, args.warmup, 0)
+    timed_kernel_ms = kernel_ms[args.warmup:]
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.kernel_launches - launches0 - args.warmup
+    # the device-timed total excludes the L2 flush: sum of per-step (kernel event time), max over ranks
+    ksum = sum(timed_kernel_ms)
+    if world > 1:
+        t = torch.tensor([ksum], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ksum = float(t.item())
+    checks = agg_dev.cpu().numpy()
+    dt_e2e = timed(step_e2e, args.steps, min(args.warmup, 1), 1000)
+
+    total_playouts = P * world * args.steps
+    value = total_playouts / dt
+    e2e = total_playouts / dt_e2e
+
+    line = None
+    if rank == 0:
+        wl = load_workload()
+        peaks = measured_peaks()
+        prop = torch.cuda.get_device_properties(local)
+        sm_count = prop.multi_processor_count
+        A = wl["algorithmic_int_ops_per_playout"]
+        k_avg_ms = ksum / args.steps
+        achieved = A * P / (k_avg_ms * 1e-3) / 1e9                      # Gop/s (algorithmic int ops)
+        peak = sm_count * 4 * 32 * peaks["sm_max_mhz"] * 1e6 / 1e9      # Gop/s: SMs x 4 schedulers x 32 lanes x clock
+        alg_bytes = stride + LEAF_RESULT_DTYPE.itemsize
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "playouts_per_gpu_per_step": P, "run_seed": RUN_SEED,
+                       "l2": "256 MiB memset between steps (inputs are 304 B; the kernel is issue-bound, not memory-bound)",
+                       "exchange": "none" if world == 1 else "NCCL all-reduce of 20 int64 per-leaf sums, once per step"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": stride * world,
+                    "d2h_bytes_per_step": LEAF_RESULT_DTYPE.itemsize * world},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "int_issue", "kernel": "orx::rollout_kernel<2,false>", "achieved": achieved, "peak": peak,
+                         "unit": "Gop/s", "frac": achieved / peak,
+                         "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']} MHz "
+                                        f"({peaks['_source']} clock, MEASURED_PEAKS.json)",
+                         "algorithmic_int_ops_per_playout": A, "kernel_ms_avg": k_avg_ms,
+                         "traffic": None,
+                         "hbm_side_check": {"algorithmic_bytes_per_launch": alg_bytes,
+                                            "achieved_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9,
+                                            "peak_gbs": peaks["hbm_gbs"]}},
+            "result_check": {"n": int(checks[0]), "wins": [int(x) for x in checks[2:8]]},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            sample = 128 * cores
+            cdt = cpu_rollouts(sample, cores)
+            line["cpu_baseline"] = {"value": sample / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} playouts of the same leaf, oracle/oponn_oracle.c -O2, {cores} threads "
+                                              "(C restatement of the Java simulator; JVM and Lux SDK unavailable)"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--playouts", type=int, default=1 << 20, help="playouts per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

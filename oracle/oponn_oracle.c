@@ -1358,6 +1358,7 @@ typedef struct BatchJob {
     const OrcCtx *ctx; const uint8_t *leaves; int n_leaves, ppl; uint64_t seed, first_game;
     OrxGameResult *games; OrxLeafResult *agg; Counters ct;
     int tid, nthreads; int stride;
+    int64_t *next; /* shared ticket counter: games are handed out one at a time so long games balance */
 } BatchJob;
 
 static void *batch_worker(void *arg)
@@ -1366,9 +1367,9 @@ static void *batch_worker(void *arg)
     Board *b = malloc(sizeof(Board));
     board_init_static(b, j->ctx);
     int64_t total = (int64_t)j->n_leaves * j->ppl;
-    /* contiguous slice per thread */
-    int64_t lo = total * j->tid / j->nthreads, hi = total * (j->tid + 1) / j->nthreads;
-    for (int64_t g = lo; g < hi; g++) {
+    for (;;) {
+        int64_t g = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (g >= total) break;
         int leaf = (int)(g / j->ppl);
         OrxGameResult r;
         run_one(b, j->ctx, j->leaves + (size_t)leaf * (size_t)j->stride, j->seed, j->first_game + (uint64_t)g, NULL, 0, &r, &j->ct);
@@ -1393,8 +1394,9 @@ int orc_rollout_batch(const OrcCtx *ctx, const uint8_t *leaves, int n_leaves, in
     BatchJob *jobs = calloc((size_t)nthreads, sizeof *jobs);
     pthread_t *th = calloc((size_t)nthreads, sizeof *th);
     OrxLeafResult *aggs = calloc((size_t)nthreads * (size_t)(n_leaves ? n_leaves : 1), sizeof *aggs);
+    int64_t next = 0;
     for (int t = 0; t < nthreads; t++) {
-        jobs[t] = (BatchJob){ ctx, leaves, n_leaves, playouts_per_leaf, seed, first_game, games, aggs + (size_t)t * (size_t)n_leaves, { 0 }, t, nthreads, L.stride };
+        jobs[t] = (BatchJob){ ctx, leaves, n_leaves, playouts_per_leaf, seed, first_game, games, aggs + (size_t)t * (size_t)n_leaves, { 0 }, t, nthreads, L.stride, &next };
         if (nthreads > 1) pthread_create(&th[t], NULL, batch_worker, &jobs[t]); else batch_worker(&jobs[t]);
     }
     if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
