@@ -12,6 +12,9 @@
 #include <vector>
 
 #define ORX_BLOCK_THREADS 128
+#ifndef ORX_MIN_BLOCKS
+#define ORX_MIN_BLOCKS 5   /* 20 warps/SM, up to 96 registers: more resident warps bought nothing (profiles/r1b) */
+#endif
 
 #include "../../include/orx.h"
 #include "orx_game.cuh"
@@ -143,7 +146,7 @@ __global__ void battles_kernel(const __grid_constant__ DevMap dm, int a, int d, 
     long long i = (long long)blockIdx.x * 4 + wid;
     if (i >= n) return;
     Stream<false> s;
-    s.init(sm[wid] + 8, sm[wid], seed, first_game + (unsigned long long)i, nullptr, 0);
+    s.init(to_saddr(sm[wid] + 8), to_saddr(sm[wid]), seed, first_game + (unsigned long long)i, nullptr, 0);
     int al = 0, dl = 0;
     if (individual) {
         if (a < 1 || a > 3 || d < 1 || d > 2) s.flags |= ORX_FLAG_ERROR;
@@ -160,7 +163,7 @@ __global__ void draws_kernel(unsigned long long seed, unsigned long long game, c
 {
     __shared__ uint32_t sm[128 + 8];
     Stream<REPLAY> s;
-    s.init(sm + 8, sm, seed, game, words, n_words);
+    s.init(to_saddr(sm + 8), to_saddr(sm), seed, game, words, n_words);
     for (int i = 0; i < n_ops; i++) {
         int op = ops[i];
         double v;
@@ -170,7 +173,7 @@ __global__ void draws_kernel(unsigned long long seed, unsigned long long game, c
         else v = (double)s.word();
         if (lane_id() == 0) out[i] = v;
     }
-    if (lane_id() == 0) { pos_flags[0] = s.pos; pos_flags[1] = s.flags; }
+    if (lane_id() == 0) { pos_flags[0] = s.pos(); pos_flags[1] = s.flags; }
 }
 
 __global__ void card_value_kernel(const __grid_constant__ DevMap dm, int pos, int32_t *out)
@@ -370,6 +373,11 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
     CKC(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
 
+    {   // floor(2^32 / b) + 1 (Stream::next_int)
+        std::vector<uint32_t> magic(ORX_MAGIC_N, 0u);
+        for (uint32_t b = 2; b < ORX_MAGIC_N; b++) magic[b] = (uint32_t)((1ull << 32) / b) + 1u;
+        CKC(cudaMemcpyToSymbol(c_magic, magic.data(), sizeof(uint32_t) * ORX_MAGIC_N));
+    }
     CKC(cudaMalloc(&c->d_blob, blob.size()));
     CKC(cudaMemcpyAsync(c->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
     dm.blob = c->d_blob;

@@ -6,6 +6,10 @@
 // shuffle / redux.  Randomness is the injected word stream of include/orx_state.h consumed
 // through java.util.Random's derivations, so a Java harness can replay a playout bit for bit.
 //
+// Shared memory is addressed through explicit 32-bit shared-window addresses (ld.shared /
+// st.shared): the generic-pointer form made ptxas rebuild the window base (S2R SR_CgaCtaId + LEA)
+// inside the attack loop (profiles/r1a).
+//
 // Reference files restated here (O/ = /root/reference/src/com/mld46/oponn/):
 //   O/BattleSim.java (whole), O/CardManager.java:283-341 ; the game itself is in orx_game.cuh
 #pragma once
@@ -17,6 +21,7 @@
 
 #define ORX_FULL 0xFFFFFFFFu
 #define ORX_TABLE_LIMIT 100
+#define ORX_MAGIC_N 1024
 
 namespace orx {
 
@@ -51,12 +56,24 @@ struct DevMap {
     uint64_t single_thr[6][2];  // floor(cdf*2^53) of BattleSim.outcomes rows (O/BattleSim.java:36-44)
 };
 
+// floor(2^32 / b) + 1 for b < ORX_MAGIC_N: u % b for u < 2^31 in four instructions (next_int)
+__constant__ uint32_t c_magic[ORX_MAGIC_N];
+
 // per-warp header words (uint32 indices into the first 32 bytes of the slice)
 enum { WH_GAUSS_LO = 0, WH_GAUSS_HI = 1, WH_HAVE_GAUSS = 2, WH_G0 = 3, WH_G1 = 4, WH_SIM_START = 5, WH_REM_COUNTRIES = 6 };
 #define ORX_WARP_HDR_BYTES 32
 
-__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31); }
+__device__ __forceinline__ int lane_id() { int l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint32_t lanemask_le() { uint32_t m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
+
+// ---- shared memory through 32-bit shared-window addresses -------------------------------------
+typedef uint32_t saddr;
+__device__ __forceinline__ saddr to_saddr(const void *p) { return (saddr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(saddr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(saddr a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(saddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(saddr a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // index of the n-th (0-based) set bit of a warp-uniform mask; n < popc(mask)
 __device__ __forceinline__ int nth_bit(uint32_t mask, int n)
@@ -83,13 +100,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 // all 32 lanes evaluate one Philox counter each: 128 words, component-major (orx_state.h)
-__device__ __noinline__ void philox_refill(uint32_t *buf, uint32_t blk, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1)
+__device__ __noinline__ void philox_refill(saddr buf, uint32_t blk, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1)
 {
     uint32_t o[4];
     int l = lane_id();
     philox4x32_10(blk * 32u + (uint32_t)l, 0u, g0, g1, k0, k1, o);
     __syncwarp();
-    buf[l] = o[0]; buf[32 + l] = o[1]; buf[64 + l] = o[2]; buf[96 + l] = o[3];
+    saddr a = buf + 4u * (uint32_t)l;
+    sts32(a, o[0]); sts32(a + 128u, o[1]); sts32(a + 256u, o[2]); sts32(a + 384u, o[3]);
     __syncwarp();
 }
 
@@ -98,40 +116,44 @@ __device__ __noinline__ void philox_refill(uint32_t *buf, uint32_t blk, uint32_t
 // ---------------------------------------------------------------------------------------
 template <bool REPLAY>
 struct Stream {
-    uint32_t *buf;          // this warp's 128-word block in shared memory
-    uint32_t *hdr;          // this warp's header words (game id, cached gaussian)
-    uint32_t  pos;          // words consumed
-    int32_t   block;        // block index held in buf, -1 = none
+    saddr     buf;          // this warp's 128-word block in shared memory
+    saddr     hdr;          // this warp's header words (game id, cached gaussian)
+    uint32_t  wi;           // counter mode: next unread word of the block (128 = block used up)
+    uint32_t  base;         // counter mode: stream position of buf[0]; replay: words consumed
     uint32_t  k0, k1;       // Philox key = seed (kernel parameter, warp-uniform)
     const uint32_t *words;  // REPLAY: explicit words
     uint32_t  n_words;
     uint32_t  flags;        // ORX_FLAG_* raised by the stream (and by the game)
 
-    __device__ __forceinline__ void init(uint32_t *b, uint32_t *h, uint64_t seed, uint64_t game, const uint32_t *w, uint32_t nw)
+    __device__ __forceinline__ void init(saddr b, saddr h, uint64_t seed, uint64_t game, const uint32_t *w, uint32_t nw)
     {
-        buf = b; hdr = h; pos = 0; block = -1; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        buf = b; hdr = h; wi = 128u; base = REPLAY ? 0u : (uint32_t)-128; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         words = w; n_words = nw; flags = 0;
         __syncwarp();
-        if (lane_id() == 0) { h[WH_G0] = (uint32_t)game; h[WH_G1] = (uint32_t)(game >> 32); h[WH_HAVE_GAUSS] = 0u; }
+        if (lane_id() == 0) { sts32(h + 4 * WH_G0, (uint32_t)game); sts32(h + 4 * WH_G1, (uint32_t)(game >> 32)); sts32(h + 4 * WH_HAVE_GAUSS, 0u); }
         __syncwarp();
     }
 
-    __device__ __forceinline__ void refill(int32_t blk)
+    __device__ __forceinline__ uint32_t pos() const { return REPLAY ? base : base + wi; }
+
+    __device__ __forceinline__ void refill()
     {
-        philox_refill(buf, (uint32_t)blk, hdr[WH_G0], hdr[WH_G1], k0, k1);
-        block = blk;
+        base += 128u;
+        philox_refill(buf, base >> 7, lds32(hdr + 4 * WH_G0), lds32(hdr + 4 * WH_G1), k0, k1);
+        wi = 0u;
     }
 
     __device__ __forceinline__ uint32_t word()
     {
-        uint32_t i = pos++;
         if (REPLAY) {
+            uint32_t i = base++;
             if (i >= n_words) { flags |= ORX_FLAG_STREAM_END; return 0u; }
             return __ldg(words + i);
         }
-        int32_t blk = (int32_t)(i >> 7);
-        if (blk != block) refill(blk);
-        return buf[i & 127u];
+        if (wi == 128u) refill();
+        uint32_t v = lds32(buf + 4u * wi);
+        wi++;
+        return v;
     }
 
     // java.util.Random.nextInt(int bound)
@@ -139,10 +161,17 @@ struct Stream {
     {
         if (bound <= 0) { flags |= ORX_FLAG_ERROR; return 0; }
         uint32_t u = word() >> 1;
-        uint32_t m = (uint32_t)bound - 1u;
-        if (((uint32_t)bound & m) == 0u) return (int)(((unsigned long long)(uint32_t)bound * u) >> 31);
+        uint32_t b = (uint32_t)bound, m = b - 1u;
+        if ((b & m) == 0u) return (int)(((unsigned long long)b * u) >> 31);
         for (;;) {
-            uint32_t r = u % (uint32_t)bound;
+            uint32_t r;
+            if (b < (uint32_t)ORX_MAGIC_N) {  // u % b by multiplication: the estimate is q or q + 1
+                uint32_t q = __umulhi(u, c_magic[b]);
+                r = u - q * b;
+                if ((int)r < 0) r += b;
+            } else {
+                r = u % b;
+            }
             if ((int)(u - r + m) >= 0) return (int)r;
             if (flags) return 0;
             u = word() >> 1;
@@ -152,9 +181,13 @@ struct Stream {
     // the 53-bit integer k of java.util.Random.nextDouble() == k * 2^-53
     __device__ __forceinline__ uint64_t next_k53()
     {
-        uint64_t hi = word() >> 6;
-        uint64_t lo = word() >> 5;
-        return (hi << 27) + lo;
+        uint32_t w0, w1;
+        if (!REPLAY && wi <= 126u) {
+            w0 = lds32(buf + 4u * wi); w1 = lds32(buf + 4u * wi + 4u); wi += 2u;
+        } else {
+            w0 = word(); w1 = word();
+        }
+        return ((uint64_t)(w0 >> 6) << 27) + (uint64_t)(w1 >> 5);
     }
     __device__ __forceinline__ double next_double() { return (double)(long long)next_k53() * 0x1.0p-53; }
 };
@@ -225,10 +258,10 @@ __device__ __noinline__ double gaussian_from_pair(double v1, double v2, double q
 template <bool REPLAY>
 __device__ __forceinline__ double next_gaussian(Stream<REPLAY> &s)
 {
-    if (s.hdr[WH_HAVE_GAUSS]) {
-        double g = __hiloint2double((int)s.hdr[WH_GAUSS_HI], (int)s.hdr[WH_GAUSS_LO]);
+    if (lds32(s.hdr + 4 * WH_HAVE_GAUSS)) {
+        double g = __hiloint2double((int)lds32(s.hdr + 4 * WH_GAUSS_HI), (int)lds32(s.hdr + 4 * WH_GAUSS_LO));
         __syncwarp();
-        if (lane_id() == 0) s.hdr[WH_HAVE_GAUSS] = 0u;
+        if (lane_id() == 0) sts32(s.hdr + 4 * WH_HAVE_GAUSS, 0u);
         __syncwarp();
         return g;
     }
@@ -243,8 +276,8 @@ __device__ __forceinline__ double next_gaussian(Stream<REPLAY> &s)
     double first = gaussian_from_pair(v1, v2, q, &second);
     __syncwarp();
     if (lane_id() == 0) {
-        s.hdr[WH_GAUSS_LO] = (uint32_t)__double2loint(second); s.hdr[WH_GAUSS_HI] = (uint32_t)__double2hiint(second);
-        s.hdr[WH_HAVE_GAUSS] = 1u;
+        sts32(s.hdr + 4 * WH_GAUSS_LO, (uint32_t)__double2loint(second)); sts32(s.hdr + 4 * WH_GAUSS_HI, (uint32_t)__double2hiint(second));
+        sts32(s.hdr + 4 * WH_HAVE_GAUSS, 1u);
     }
     __syncwarp();
     return first;
@@ -308,49 +341,63 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
         }
     } else {
         int ra = attackers, rd = defenders;
-        // single rolls while either side is above 100 (O/BattleSim.java:99-116), up to 32 rolls per
-        // step: every lane rolls with the next double of the block, and exactly the rolls the
-        // reference's loop would have played are consumed.
+        // Single rolls while either side is above 100 (O/BattleSim.java:99-116).  Three ways through, all
+        // consuming exactly the doubles the reference's loop would:
+        //   scalar  one roll per trip when a side is about to run out (<= 2 armies), at a block boundary, or on replay;
+        //   block   up to 64 rolls (2 per lane) when no roll of the step can end the loop or change the dice;
+        //   scan    up to 32 rolls (1 per lane): the first roll after which the loop would stop is found by ballot.
         while ((ra > 100 || rd > 100) && ra > 0 && rd > 0 && !s.flags) {
             int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
             int avail = 0;
-            if (!REPLAY) {
-                if ((int32_t)(s.pos >> 7) != s.block) s.refill((int32_t)(s.pos >> 7));
-                avail = (int)(128u - (s.pos & 127u)) >> 1;
-                if (avail > 32) avail = 32;
+            if (!REPLAY && ra > 2 && rd > 2) {
+                if (s.wi == 128u) s.refill();
+                avail = (int)(128u - s.wi) >> 1;
             }
-            if (avail == 0) {  // block boundary (or replay mode): one roll through the scalar path
+            if (avail == 0) {
                 int x = single_roll(dm, pa, pd, s.next_k53());
                 attackerLosses += x; defenderLosses += n - x; ra -= x; rd -= n - x;
                 continue;
             }
+            // here pa == 3 and pd == 2: thresholds of row 5
+            const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
             int l = lane_id();
-            uint32_t base = (s.pos & 127u) + 2u * (uint32_t)l;
-            uint64_t k = 0;
-            if (l < avail) k = ((uint64_t)(s.buf[base] >> 6) << 27) + (uint64_t)(s.buf[base + 1] >> 5);
-            int x = single_roll(dm, pa, pd, k);
-            if (avail == 32 && ra >= 65 && rd >= 64 && (ra > 162 || rd > 162)) {
-                // no roll of this step can end the loop or change the dice: 3 v 2 throughout
-                int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 64 - la;
+            saddr p0 = s.buf + 4u * s.wi + 8u * (uint32_t)l;
+            int lo = ra < rd ? ra : rd, hi = ra < rd ? rd : ra;
+            int slack = 2 * (avail - 1);  // armies lost before the last roll of the step, at most
+            if (avail >= 32 && ra - slack >= 3 && rd - slack >= 2 && hi - slack > 100) {
+                int x = 0;
+                {
+                    uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
+                    x = (k > t0) + (k > t1);
+                }
+                if (l + 32 < avail) {
+                    uint64_t k = ((uint64_t)(lds32(p0 + 256u) >> 6) << 27) + (uint64_t)(lds32(p0 + 260u) >> 5);
+                    x += (k > t0) + (k > t1);
+                }
+                int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 2 * avail - la;
                 attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
-                s.pos += 64u;
+                s.wi += 2u * (uint32_t)avail;
                 continue;
             }
-            uint32_t packed = (uint32_t)x | ((uint32_t)(n - x) << 16);  // (attacker, defender) losses
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t up = __shfl_up_sync(ORX_FULL, packed, o);
-                if (l >= o) packed += up;
+            (void)lo;
+            if (avail > 32) avail = 32;
+            int x = 0;
+            if (l < avail) {
+                uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
+                x = (k > t0) + (k > t1);
             }
-            int ra_l = ra - (int)(packed & 0xFFFFu), rd_l = rd - (int)(packed >> 16);
-            bool go_on = (ra_l > 100 || rd_l > 100) && ra_l > 0 && rd_l > 0 &&
-                         (ra_l < 3 ? ra_l : 3) == pa && (rd_l < 2 ? rd_l : 2) == pd;
+            // attacker losses up to and including roll l, from two ballots (x is 0, 1 or 2)
+            uint32_t b1 = __ballot_sync(ORX_FULL, x >= 1), b2 = __ballot_sync(ORX_FULL, x == 2);
+            uint32_t le = lanemask_le();
+            int cumA = __popc(b1 & le) + __popc(b2 & le);
+            int ra_l = ra - cumA, rd_l = rd - (2 * (l + 1) - cumA);
+            bool go_on = (ra_l > 100 || rd_l > 100) && ra_l >= 3 && rd_l >= 2;
             uint32_t stop = __ballot_sync(ORX_FULL, !go_on || l >= avail - 1);
             int last = __ffs(stop) - 1;  // rolls 0..last are played
-            uint32_t tot = __shfl_sync(ORX_FULL, packed, last);
-            int la = (int)(tot & 0xFFFFu), ld = (int)(tot >> 16);
+            uint32_t upto = 0xFFFFFFFFu >> (31 - last);
+            int la = __popc(b1 & upto) + __popc(b2 & upto), ld = 2 * (last + 1) - la;
             attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
-            s.pos += 2u * (uint32_t)(last + 1);
+            s.wi += 2u * (uint32_t)(last + 1);
         }
         if (ra != 0 && rd != 0 && !s.flags) {
             if (ra < 0 || rd < 0 || ra > ORX_TABLE_LIMIT || rd > ORX_TABLE_LIMIT) {

@@ -31,10 +31,9 @@ struct RolloutArgs {
 template <int NWT, bool REPLAY>
 struct Game {
     const DevMap &dm;
-    const uint8_t *sb;      // static map image in shared memory
-    int32_t *armies;
-    uint8_t *owner, *alist, *cards;
-    uint32_t *hdr;
+    // 32-bit shared-window addresses: the static map image (per block) and this warp's slice
+    saddr s_adj, s_deg, s_sym, s_nbr, s_cont, s_bonus;
+    saddr a_arm, a_own, a_alist, a_cards, a_hdr;
     Stream<REPLAY> s;
     int lane;
 
@@ -50,38 +49,42 @@ struct Game {
     __device__ __forceinline__ void fail() { s.flags |= ORX_FLAG_ERROR; }
 
     // ---- static map accessors --------------------------------------------------------
-    __device__ __forceinline__ int adj(int t, int j) const { return sb[dm.adj_off + t * dm.degp + j]; }
-    __device__ __forceinline__ int deg(int t) const { return sb[dm.deg_off + t]; }
-    __device__ __forceinline__ uint32_t symbit(int card) const { return card == (int)ORX_CARD_WILD ? 8u : (uint32_t)sb[dm.sym_off + card]; }
-    __device__ __forceinline__ uint32_t nbr(int w, int t) const { return ((const uint32_t *)(sb + dm.nbr_off))[w * dm.NP + t]; }
-    __device__ __forceinline__ uint32_t contmask(int c, int w) const { return ((const uint32_t *)(sb + dm.cont_off))[c * NWT + w]; }
+    __device__ __forceinline__ int adj(int t, int j) const { return (int)lds8(s_adj + (uint32_t)(t * dm.degp + j)); }
+    __device__ __forceinline__ int deg(int t) const { return (int)lds8(s_deg + (uint32_t)t); }
+    __device__ __forceinline__ uint32_t symbit(int card) const { return card == (int)ORX_CARD_WILD ? 8u : lds8(s_sym + (uint32_t)card); }
+    __device__ __forceinline__ uint32_t nbr(int w, int t) const { return lds32(s_nbr + 4u * (uint32_t)(w * (32 * NWT) + t)); }
+    __device__ __forceinline__ uint32_t contmask(int c, int w) const { return lds32(s_cont + 4u * (uint32_t)(c * NWT + w)); }
 
     // ---- shared-memory helpers (one writer lane, fenced on both sides) ------------------
-    __device__ __forceinline__ void set_armies(int t, int v) { __syncwarp(); if (lane == 0) armies[t] = v; __syncwarp(); }
-    __device__ __forceinline__ void set_owner(int t, int v) { __syncwarp(); if (lane == 0) owner[t] = (uint8_t)v; __syncwarp(); }
+    __device__ __forceinline__ int armies(int t) const { return (int)lds32(a_arm + 4u * (uint32_t)t); }
+    __device__ __forceinline__ int owner(int t) const { return (int)lds8(a_own + (uint32_t)t); }
+    __device__ __forceinline__ uint32_t hdr(int i) const { return lds32(a_hdr + 4u * (uint32_t)i); }
+    __device__ __forceinline__ void set_hdr(int i, uint32_t v) { __syncwarp(); if (lane == 0) sts32(a_hdr + 4u * (uint32_t)i, v); __syncwarp(); }
+    __device__ __forceinline__ void set_armies(int t, int v) { __syncwarp(); if (lane == 0) sts32(a_arm + 4u * (uint32_t)t, (uint32_t)v); __syncwarp(); }
+    __device__ __forceinline__ void set_owner(int t, int v) { __syncwarp(); if (lane == 0) sts8(a_own + (uint32_t)t, (uint32_t)v); __syncwarp(); }
     template <typename T> __device__ __forceinline__ T from_lane(T v, int l) const { return __shfl_sync(ORX_FULL, v, l); }
 
     // ---- ordered lists (java.util.List<Card>): list li < P is player li's hand, li == P the sim deck ----
-    __device__ __forceinline__ uint8_t *list(int li) const { return cards + li * dm.cap; }
+    __device__ __forceinline__ saddr list(int li) const { return a_cards + (uint32_t)(li * dm.cap); }
     __device__ __forceinline__ int list_len(int li) const { return from_lane(ncard, li); }
     __device__ __forceinline__ void list_add(int li, int card)
     {
         int n = list_len(li);
         if (n >= dm.cap) { fail(); return; }
         __syncwarp();
-        if (lane == 0) list(li)[n] = (uint8_t)card;
+        if (lane == 0) sts8(list(li) + (uint32_t)n, (uint32_t)card);
         if (lane == li) ncard++;
         __syncwarp();
     }
     // remove(int index) on a byte list of length n held at p
-    __device__ __forceinline__ int bytes_remove_at(uint8_t *p, int n, int i)
+    __device__ __forceinline__ int bytes_remove_at(saddr p, int n, int i)
     {
-        int c = p[i];
+        int c = (int)lds8(p + (uint32_t)i);
         for (int base = i; base < n - 1; base += 32) {
             int idx = base + lane;
-            uint8_t v = idx < n - 1 ? p[idx + 1] : (uint8_t)0;
+            uint32_t v = idx < n - 1 ? lds8(p + (uint32_t)idx + 1u) : 0u;
             __syncwarp();
-            if (idx < n - 1) p[idx] = v;
+            if (idx < n - 1) sts8(p + (uint32_t)idx, v);
             __syncwarp();
         }
         return c;
@@ -99,7 +102,7 @@ struct Game {
     __device__ __forceinline__ void owned_mask(int player, uint32_t (&m)[NWT]) const
     {
 #pragma unroll
-        for (int w = 0; w < NWT; w++) m[w] = __ballot_sync(ORX_FULL, owner[w * 32 + lane] == player);
+        for (int w = 0; w < NWT; w++) m[w] = __ballot_sync(ORX_FULL, owner(w * 32 + lane) == player);
     }
     // owned territories with at least one out-neighbour not owned (SimRandom.java:68-82,250-262)
     __device__ __forceinline__ void border_mask(const uint32_t (&mine)[NWT], bool need_two, uint32_t (&b)[NWT]) const
@@ -110,7 +113,7 @@ struct Game {
             uint32_t enemy = 0;
 #pragma unroll
             for (int w2 = 0; w2 < NWT; w2++) enemy |= nbr(w2, t) & ~mine[w2];
-            bool f = ((mine[w] >> lane) & 1u) && enemy != 0u && (!need_two || armies[t] > 1);
+            bool f = ((mine[w] >> lane) & 1u) && enemy != 0u && (!need_two || armies(t) > 1);
             b[w] = __ballot_sync(ORX_FULL, f);
         }
     }
@@ -142,19 +145,19 @@ struct Game {
     // the pick-th one in lexicographic order (Card.containsASet / Card.getRandomSet)
     __device__ __forceinline__ int scan_sets(int n, int pick, int idx[3])
     {
-        const uint8_t *h = list(cp);
+        saddr h = list(cp);
         // symbol bits of the hand, staged in the (idle) attackers-list buffer
         __syncwarp();
-        for (int base = 0; base < n; base += 32) { int i = base + lane; if (i < n) alist[i] = (uint8_t)symbit(h[i]); }
+        for (int base = 0; base < n; base += 32) { int i = base + lane; if (i < n) sts8(a_alist + (uint32_t)i, symbit((int)lds8(h + (uint32_t)i))); }
         __syncwarp();
         int count = 0;
         for (int i = 0; i < n - 2; i++) {
-            uint32_t si = alist[i];
+            uint32_t si = lds8(a_alist + (uint32_t)i);
             for (int j = i + 1; j < n - 1; j++) {
-                uint32_t sij = si | alist[j];
+                uint32_t sij = si | lds8(a_alist + (uint32_t)j);
                 for (int kb = j + 1; kb < n; kb += 32) {
                     int k = kb + lane;
-                    bool ok = k < n && is_set_bits(sij | alist[k]);
+                    bool ok = k < n && is_set_bits(sij | lds8(a_alist + (uint32_t)(k < n ? k : 0)));
                     uint32_t m = __ballot_sync(ORX_FULL, ok);
                     int c = __popc(m);
                     if (pick >= count && pick < count + c) { idx[0] = i; idx[1] = j; idx[2] = kb + nth_bit(m, pick - count); }
@@ -176,8 +179,8 @@ struct Game {
     // SimulationBoard.cashCards (SimulationBoard.java:577-618) for hand positions i<j<k
     __device__ __forceinline__ void cash_cards(const int idx[3])
     {
-        const uint8_t *h = list(cp);
-        int c0 = h[idx[0]], c1 = h[idx[1]], c2 = h[idx[2]];
+        saddr h = list(cp);
+        int c0 = (int)lds8(h + (uint32_t)idx[0]), c1 = (int)lds8(h + (uint32_t)idx[1]), c2 = (int)lds8(h + (uint32_t)idx[2]);
         list_remove_at(cp, idx[2]); list_remove_at(cp, idx[1]); list_remove_at(cp, idx[0]);
         list_add(dm.P, c0); list_add(dm.P, c1); list_add(dm.P, c2);  // CardManager.simCash :265-276
         placeable += card_cash_value(dm, cardpos, s.flags);
@@ -185,7 +188,7 @@ struct Game {
         int cs[3] = { c0, c1, c2 };
 #pragma unroll
         for (int q = 0; q < 3; q++)
-            if (cs[q] != (int)ORX_CARD_WILD && owner[cs[q]] == cp) set_armies(cs[q], armies[cs[q]] + 2);
+            if (cs[q] != (int)ORX_CARD_WILD && owner(cs[q]) == cp) set_armies(cs[q], armies(cs[q]) + 2);
     }
 
     // SimRandom.cardsPhase (SimRandom.java:36-49)
@@ -233,7 +236,7 @@ struct Game {
             int i = s.next_int(n);
             if (s.flags) return;
             int t = nth_territory(cand, i);
-            set_armies(t, armies[t] + k);
+            set_armies(t, armies(t) + k);
             placeable -= k;
             if (phase == ORX_PHASE_INITIAL_PLACEMENT && lane == cp) ialp -= k;
             n_armies -= k;
@@ -261,13 +264,13 @@ struct Game {
     // currentContinentBonuses[c] (recalculateContinentBonuses :956-963), rows precomputed on the host
     __device__ __forceinline__ int current_bonus(int c) const
     {
-        if (dm.cont_inc == 0) return ((const int32_t *)(sb + dm.bonus_off))[c];
-        int e = (int)hdr[WH_SIM_START] + simTurn - 1; if (e < 0) e = 0;
+        if (dm.cont_inc == 0) return (int)lds32(s_bonus + 4u * (uint32_t)c);
+        int e = (int)hdr(WH_SIM_START) + simTurn - 1; if (e < 0) e = 0;
         return __ldg(dm.bonus_table + e * dm.C + c);
     }
     __device__ __forceinline__ void recalculate_bonuses()
     {
-        int e = (int)hdr[WH_SIM_START] + simTurn - 1;
+        int e = (int)hdr(WH_SIM_START) + simTurn - 1;
         if (dm.cont_inc != 0 && e >= ORX_BONUS_ROUNDS) fail();  // engine table limit
     }
 
@@ -282,23 +285,23 @@ struct Game {
         if (dst != player) {
             int nsrc = list_len(player), ndst = list_len(dst);
             if (ndst + nsrc > dm.cap) { fail(); return; }
-            const uint8_t *src = list(player); uint8_t *d = list(dst);
+            saddr src = list(player), d = list(dst);
             __syncwarp();
-            for (int base = 0; base < nsrc; base += 32) { int i = base + lane; if (i < nsrc) d[ndst + i] = src[i]; }
+            for (int base = 0; base < nsrc; base += 32) { int i = base + lane; if (i < nsrc) sts8(d + (uint32_t)(ndst + i), lds8(src + (uint32_t)i)); }
             __syncwarp();
             if (lane == dst) ncard += nsrc;
             if (lane == player) ncard = 0;  // the reference leaves a stale copy that nothing reads
         }
         if (remaining == 1) {
             if (lane == cp) pot = -1;
-            if (!termSet) { termSet = true; termPos = s.pos; }
+            if (!termSet) { termSet = true; termPos = s.pos(); }
         }
     }
 
     // SimulationBoard.executeAttack (:758-780): losses for the armies on attackingCC / defendingCC
     __device__ __forceinline__ void execute_attack(int A, int D, int &al, int &dl)
     {
-        int a = armies[A] - 1, d = armies[D];
+        int a = armies(A) - 1, d = armies(D);
         if (attackUntilDead) {
             simulate_battle(dm, s, a, d, al, dl);
         } else {
@@ -312,7 +315,7 @@ struct Game {
     // SimRandom.moveArmiesIn (SimRandom.java:144-155) + executeInvasion (:814-825)
     __device__ __forceinline__ void invade(int A, int D)
     {
-        int aArm = armies[A];
+        int aArm = armies(A);
         int available = aArm - 1;
         if (available == 0) { fail(); return; }
         int mn = available < 3 ? available : 3;
@@ -320,7 +323,7 @@ struct Game {
         int lo = aArm - 1 < 3 ? aArm - 1 : 3, hi = aArm - 1;
         int inv = req > lo ? req : lo; if (inv > hi) inv = hi;
         __syncwarp();
-        if (lane == 0) { armies[D] = inv; armies[A] = aArm - inv; }
+        if (lane == 0) { sts32(a_arm + 4u * (uint32_t)D, (uint32_t)inv); sts32(a_arm + 4u * (uint32_t)A, (uint32_t)(aArm - inv)); }
         __syncwarp();
     }
 
@@ -345,55 +348,65 @@ struct Game {
         __syncwarp();
 #pragma unroll
         for (int w = 0; w < NWT; w++) {
-            if ((att[w] >> lane) & 1u) alist[nAtt + __popc(att[w] & lanemask_lt())] = (uint8_t)(w * 32 + lane);
+            if ((att[w] >> lane) & 1u) sts8(a_alist + (uint32_t)(nAtt + __popc(att[w] & lanemask_lt())), (uint32_t)(w * 32 + lane));
             nAtt += __popc(att[w]);
         }
         __syncwarp();
+        attackUntilDead = 1;
         uint32_t guard = 0;
         while (nAtt > 0 && !s.flags) {
             if (++guard > (1u << 24)) { fail(); break; }
             int ai = s.next_int(nAtt);
-            int A = alist[ai];
+            int A = (int)lds8(a_alist + (uint32_t)ai);
             // possibleDefenders: non-owned out-neighbours in getAdjoiningList() order
             int dg = deg(A);
-            int nb = lane < dg ? adj(A, lane) : 0;
-            bool enemy = lane < dg && owner[nb] != cp;
+            int nb = 0;
+            bool enemy = false;
+            if (lane < dg) { nb = adj(A, lane); enemy = owner(nb) != cp; }
             uint32_t dmask = __ballot_sync(ORX_FULL, enemy);
             int nDef = __popc(dmask);
-            if (nDef == 0) { bytes_remove_at(alist, nAtt, ai); nAtt--; continue; }
+            if (nDef == 0) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; continue; }
             int D = from_lane(nb, nth_bit(dmask, s.next_int(nDef)));
             // SimulationBoard.attack: setupAttack, executeAttack, finishAttack
-            attackUntilDead = 1;
+            saddr pA = a_arm + 4u * (uint32_t)A, pD = a_arm + 4u * (uint32_t)D;
+            int aArm = (int)lds32(pA), dArm = (int)lds32(pD);
             int al, dl;
-            execute_attack(A, D, al, dl);
+            simulate_battle(dm, s, aArm - 1, dArm, al, dl);
             if (s.flags) return;
-            int aArm = armies[A] - al, dArm = armies[D] - dl;
-            __syncwarp();
-            if (lane == 0) { armies[A] = aArm; armies[D] = dArm; }
-            __syncwarp();
+            aArm -= al; dArm -= dl;
             if (dArm == 0) {
                 // setupInvasion (:797-812)
-                int dp = owner[D];
+                int dp = owner(D);
                 if (lane == cp) pc++;
                 if (lane == dp) pc--;
-                set_owner(D, cp);
-                attackingPlayer = cp; defendingPlayer = dp;
-                invade(A, D);
-                if (s.flags) return;
-                finish_invasion();
-                if (s.flags) return;
+                // SimRandom.moveArmiesIn (SimRandom.java:144-155) + executeInvasion (:814-825)
+                int available = aArm - 1;
+                if (available == 0) { fail(); return; }
+                int mn = available < 3 ? available : 3;
+                int inv = mn + (mn == available ? 0 : s.next_int(available - mn));  // already within [min(avail,3), avail]
+                aArm -= inv; dArm = inv;
+                __syncwarp();
+                if (lane == 0) { sts32(pA, (uint32_t)aArm); sts32(pD, (uint32_t)dArm); sts8(a_own + (uint32_t)D, (uint32_t)cp); }
+                __syncwarp();
+                // finishInvasion (:827-841)
+                if (from_lane(pc, dp) == 0) { player_defeated(dp, cp); if (s.flags) return; }
+                hasInvaded = 1;
                 // result == DEFENDERS_DESTROYED (SimRandom.java:127-137)
-                if (armies[A] == 1) { bytes_remove_at(alist, nAtt, ai); nAtt--; }
-                if (armies[D] > 1) {
+                if (aArm == 1) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; }
+                if (dArm > 1) {
                     if (nAtt >= dm.cap) { fail(); return; }
-                    __syncwarp(); if (lane == 0) alist[nAtt] = (uint8_t)D; __syncwarp();
+                    __syncwarp(); if (lane == 0) sts8(a_alist + (uint32_t)nAtt, (uint32_t)D); __syncwarp();
                     nAtt++;
                 }
             } else {
-                attackState = ORX_ATTACK_START;
-                if (aArm == 1) { bytes_remove_at(alist, nAtt, ai); nAtt--; }  // ATTACKERS_DESTROYED
+                __syncwarp();
+                if (lane == 0) { sts32(pA, (uint32_t)aArm); sts32(pD, (uint32_t)dArm); }
+                __syncwarp();
+                if (aArm == 1) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; }  // ATTACKERS_DESTROYED
             }
         }
+        attackState = ORX_ATTACK_START;
+        attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
     }
 
     // tearDownAttackPhase (:884-896)
@@ -412,14 +425,14 @@ struct Game {
     {
         int mysum = 0;
 #pragma unroll
-        for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N) mysum += armies[t]; }
+        for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N) mysum += armies(t); }
         int total = (int)__reduce_add_sync(ORX_FULL, (unsigned)mysum);
         if (total <= 100000) return;
         int maxArmies = 0, maxPlayer = -1;
         for (int p = 0; p < dm.P; p++) {
             int ps = 0;
 #pragma unroll
-            for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N && owner[t] == p) ps += armies[t]; }
+            for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N && owner(t) == p) ps += armies(t); }
             int tot = (int)__reduce_add_sync(ORX_FULL, (unsigned)ps);
             if (tot > maxArmies) { maxPlayer = p; maxArmies = tot; }
         }
@@ -449,7 +462,7 @@ struct Game {
     }
     __device__ __forceinline__ void tear_down_country_selection_phase()
     {
-        if ((int)hdr[WH_REM_COUNTRIES] == 0) { phase = ORX_PHASE_INITIAL_PLACEMENT; cp = 0; }
+        if ((int)hdr(WH_REM_COUNTRIES) == 0) { phase = ORX_PHASE_INITIAL_PLACEMENT; cp = 0; }
     }
     __device__ __forceinline__ void select_country()
     {
@@ -461,9 +474,7 @@ struct Game {
         int cc = nth_territory(free_, i);
         set_owner(cc, cp);
         if (lane == cp) { pc++; ialp--; }
-        __syncwarp();
-        if (lane == 0) hdr[WH_REM_COUNTRIES] -= 1u;
-        __syncwarp();
+        set_hdr(WH_REM_COUNTRIES, hdr(WH_REM_COUNTRIES) - 1u);
         cp = (cp + 1) % dm.P;
     }
     __device__ __forceinline__ void tear_down_initial_placement_phase()
@@ -518,7 +529,7 @@ struct Game {
                 if (!(o < P || (o == (int)ORX_OWNER_NONE && h_phase == ORX_PHASE_COUNTRY_SELECTION))) badt = true;
                 if (a < 1 || a > ORX_MAX_ARMIES) badt = true;
             }
-            owner[t] = (uint8_t)o; armies[t] = a;
+            sts8(a_own + (uint32_t)t, (uint32_t)o); sts32(a_arm + 4u * (uint32_t)t, (uint32_t)a);
         }
         // cards: hand then deck (CardManager.simReset :240-248)
         const uint8_t *lc = leaf + dm.off_cards;
@@ -527,7 +538,7 @@ struct Game {
             if (i < n_hand + n_deck && i < N + 2) {
                 int c = __ldg(lc + i);
                 if (!(c < N || c == (int)ORX_CARD_WILD)) badt = true;
-                if (!bad) { if (i < n_hand) list(h_cp)[i] = (uint8_t)c; else list(P)[i - n_hand] = (uint8_t)c; }
+                if (!bad) { if (i < n_hand) sts8(list(h_cp) + (uint32_t)i, (uint32_t)c); else sts8(list(P) + (uint32_t)(i - n_hand), (uint32_t)c); }
             }
         }
         int my_ncards = lane < P ? (int)__ldg(leaf + dm.off_ncards + lane) : 0;
@@ -541,7 +552,7 @@ struct Game {
         termSet = false; termPos = 0;
         pot = 0; ialp = 0;
         ncard = lane == cp ? n_hand : (lane == P ? n_deck : 0);
-        if (lane == 0) { hdr[WH_SIM_START] = (uint32_t)turn_count; hdr[WH_REM_COUNTRIES] = 0u; }
+        if (lane == 0) { sts32(a_hdr + 4u * WH_SIM_START, (uint32_t)turn_count); sts32(a_hdr + 4u * WH_REM_COUNTRIES, 0u); }
         __syncwarp();
 
         // setupCardState (:205-227): hidden hands are dealt at random, in player order
@@ -576,9 +587,7 @@ struct Game {
             uint32_t free_[NWT];
             owned_mask((int)ORX_OWNER_NONE, free_);
             ialp = start - pc;
-            __syncwarp();
-            if (lane == 0) hdr[WH_REM_COUNTRIES] = (uint32_t)count_bits(free_);
-            __syncwarp();
+            set_hdr(WH_REM_COUNTRIES, (uint32_t)count_bits(free_));
             break;
         }
         case ORX_PHASE_INITIAL_PLACEMENT: {
@@ -586,7 +595,7 @@ struct Game {
             for (int p = 0; p < P; p++) {
                 int ps = 0;
 #pragma unroll
-                for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (owner[t] == p) ps += armies[t]; }
+                for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (owner(t) == p) ps += armies(t); }
                 int tot = (int)__reduce_add_sync(ORX_FULL, (unsigned)ps);
                 if (lane == p) mine_total = tot;
             }
@@ -602,7 +611,7 @@ struct Game {
             hasInvaded = h_inv != 0;
             attackState = h_astate;
             attackingCC = h_acc; defendingCC = h_dcc;
-            if (attackingCC != -1) { attackingPlayer = owner[attackingCC]; defendingPlayer = h_dp; }
+            if (attackingCC != -1) { attackingPlayer = owner(attackingCC); defendingPlayer = h_dp; }
             if (h_astate == ORX_ATTACK_INVADE) {
                 if (defendingPlayer < 0 || defendingPlayer >= P) { fail(); return; }
                 if (from_lane(pc, defendingPlayer) == 0) remaining++;
@@ -655,9 +664,9 @@ struct Game {
                         int al, dl;
                         execute_attack(attackingCC, defendingCC, al, dl);
                         if (s.flags) break;
-                        int aArm = armies[attackingCC] - al, dArm = armies[defendingCC] - dl;  // finishAttack
+                        int aArm = armies(attackingCC) - al, dArm = armies(defendingCC) - dl;  // finishAttack
                         set_armies(attackingCC, aArm); set_armies(defendingCC, dArm);
-                        attackState = armies[defendingCC] == 0 ? ORX_ATTACK_INVADE : ORX_ATTACK_START;
+                        attackState = armies(defendingCC) == 0 ? ORX_ATTACK_INVADE : ORX_ATTACK_START;
                     }
                     if (attackState == ORX_ATTACK_INVADE) {
                         // no setupInvasion() on this path: SURVEY 8.1 quirk 1
@@ -702,13 +711,13 @@ struct Game {
 #pragma unroll
             for (int w = 0; w < NWT; w++) {
                 int t = w * 32 + lane;
-                if (t < dm.N) hsum += orx_mix((uint32_t)t, (uint32_t)owner[t], (uint32_t)armies[t]);
+                if (t < dm.N) hsum += orx_mix((uint32_t)t, (uint32_t)owner(t), (uint32_t)armies(t));
             }
             hsum = __reduce_add_sync(ORX_FULL, hsum);
         }
         int my_pot = (!dead && lane < dm.P) ? pot : 0;
         int turns = dead ? 0 : simTurn;
-        uint32_t spos = dead ? 0u : (termSet ? termPos : s.pos);
+        uint32_t spos = dead ? 0u : (termSet ? termPos : s.pos());
         if (out) {
             uint32_t v = lane < ORX_MAX_PLAYERS ? (uint32_t)my_pot
                        : lane == 8 ? (uint32_t)turns : lane == 9 ? flags : lane == 10 ? spos : hsum;
@@ -728,7 +737,7 @@ struct Game {
 
 // The rollout kernel: persistent warps pull game indices from a ticket counter.
 template <int NWT, bool REPLAY>
-__global__ void __launch_bounds__(ORX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ RolloutArgs ar)
+__global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ RolloutArgs ar)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // stage the static map image
@@ -741,14 +750,14 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS) rollout_kernel(const __grid
     uint8_t *slice = smem + dm.blob_bytes + wid * dm.w_bytes;
 
     Game<NWT, REPLAY> g(dm);
-    g.sb = smem;
+    const saddr sbase = to_saddr(smem), wbase = to_saddr(slice);
+    g.s_adj = sbase + (uint32_t)dm.adj_off; g.s_deg = sbase + (uint32_t)dm.deg_off; g.s_sym = sbase + (uint32_t)dm.sym_off;
+    g.s_nbr = sbase + (uint32_t)dm.nbr_off; g.s_cont = sbase + (uint32_t)dm.cont_off; g.s_bonus = sbase + (uint32_t)dm.bonus_off;
     g.lane = lane_id();
-    g.hdr = (uint32_t *)slice;
-    g.armies = (int32_t *)(slice + dm.w_armies);
-    g.owner = slice + dm.w_owner;
-    g.alist = slice + dm.w_alist;
-    g.cards = slice + dm.w_cards;
-    uint32_t *rng = (uint32_t *)(slice + dm.w_rng);
+    g.a_hdr = wbase;
+    g.a_arm = wbase + (uint32_t)dm.w_armies; g.a_own = wbase + (uint32_t)dm.w_owner;
+    g.a_alist = wbase + (uint32_t)dm.w_alist; g.a_cards = wbase + (uint32_t)dm.w_cards;
+    const saddr rng = wbase + (uint32_t)dm.w_rng;
 
     for (;;) {
         unsigned long long idx = 0;
@@ -757,7 +766,7 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS) rollout_kernel(const __grid
         if (idx >= ar.total) break;
         unsigned long long leaf_i = REPLAY ? idx : idx / (unsigned long long)ar.playouts_per_leaf;
         const uint8_t *leaf = ar.leaves + leaf_i * (unsigned long long)dm.leaf_stride;
-        g.s.init(rng, g.hdr, ar.seed, ar.first_game + idx,
+        g.s.init(rng, g.a_hdr, ar.seed, ar.first_game + idx,
                  REPLAY ? ar.words + idx * (unsigned long long)ar.words_per_game : nullptr, ar.words_per_game);
         g.simTurn = 0; g.pot = 0; g.termSet = false; g.termPos = 0;
         g.setup_state(leaf);

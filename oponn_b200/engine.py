@@ -35,7 +35,7 @@ class OrxError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    return os.environ.get("ORX_LIB", _build.LIB)
 
 
 def load_library():
