@@ -1,0 +1,101 @@
+"""Hand-derived playouts: each scenario is (map, rules, leaf, words, expected result fields).  The expectations
+were worked out by hand from the reference's source (citations in the comments), not produced by the oracle;
+they pin oracle and CUDA engine alike.  Table rows come from battlesim_ref.numpy_outcome_table (an independent
+restatement of BattleSim.generateAttackOutcomes)."""
+import numpy as np
+
+from battlesim_ref import numpy_outcome_table
+from oponn_b200.state import (ATTACK_EXECUTE, CARD_WILD, PHASE_ATTACK, PHASE_CARDS, PHASE_PLACEMENT, BoardState, RiskMap,
+                              Rules)
+from scripted import Script, board_hash
+
+
+def line4(n_players=2):
+    # 0 - 1 - 2 - 3 ; continents {0,1} bonus 2 and {2,3} bonus 3
+    return RiskMap(name="line4", n_players=n_players, adjacency=[[1], [0, 2], [1, 3], [2]], continent=[0, 0, 1, 1],
+                   continent_bonus=[2, 3])
+
+
+def first_row(a, d):
+    p, al, dl, inv = numpy_outcome_table(a, d)[0]
+    return al, dl, inv
+
+
+def scenario_sweep():
+    """PLACEMENT catch-up, two conquests, elimination, drain of the attackers list."""
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 5, 2, 1], currentPlayer=0, currentPhase=PHASE_PLACEMENT,
+                      numberOfPlaceableArmies=3, playerNumberOfCards=[0, 0])
+    assert first_row(7, 2) == (0, 2, True) and first_row(4, 1) == (0, 1, True)
+    s = Script()
+    s.int(3, 2).int(1, 0)          # SimRandom.place: k = 1 + 2 = 3 on candidates[0] = territory 1  -> armies[1] = 8
+    s.int(1, 0).int(1, 0)          # attackers [1] -> A = 1 ; defenders of 1 (adjacency order [0, 2], enemy only) = [2]
+    s.double_k(0)                  # battle 7 v 2: r = 0 -> first row (0, 2): conquered
+    s.int(4, 2)                    # moveArmiesIn: avail 7, min 3, 3 + nextInt(4) = 5 -> armies [1, 3, 5, 1]
+    s.int(2, 1).int(1, 0)          # attackers [1, 2] -> A = 2 ; defenders [3]
+    s.double_k(0)                  # battle 4 v 1 -> (0, 1): conquered; avail = 4, min 3, 3 + nextInt(1)
+    s.int(1, 0)                    #   -> 3 move in: armies [1, 3, 2, 3]; player 1 has no territory: defeated
+    term = len(s.words)            # playerOutOnTurn[0] = -1 is written here (SimulationBoard.java:862-866)
+    s.int(3, 0).int(2, 0).int(1, 0)  # the phase still drains [1, 2, 3]: no defenders anywhere -> three removals
+    exp = dict(pot=[-1, 0], turns=0, flags=0, stream_pos=term, hash=board_hash([0, 0, 0, 0], [1, 3, 2, 3]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_catchup_execute_keeps_owner():
+    """a leaf in ATTACK/EXECUTE that conquers runs executeInvasion without setupInvasion
+    (SimulationBoard.java:402-411): the defender keeps the territory and receives the invading armies."""
+    m, r = line4(), Rules(use_cards=False, max_player_turns=1)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 8, 2, 3], currentPlayer=0, currentPhase=PHASE_ATTACK,
+                      attackState=ATTACK_EXECUTE, attackingCC=1, defendingCC=2, defendingPlayer=1, attackUntilDead=True,
+                      playerNumberOfCards=[0, 0])
+    al, dl, inv = first_row(2, 5)
+    assert (al, dl, inv) == (2, 0, False)
+    s = Script()
+    s.double_k(0)                  # executeAttack 7 v 2 -> (0, 2): armies[2] = 0 -> INVADE
+    s.int(4, 2)                    # moveArmiesIn 3 + 2 = 5: armies [1, 3, 5, 3], owner[2] is STILL player 1
+    s.int(1, 0).int(1, 0)          # attackPhase: attackers [1] (3 armies, enemy neighbour 2); defenders [2]
+    s.double_k(0)                  # battle 2 v 5 -> first row (2, 0): attackers destroyed -> armies[1] = 1, list empty
+    exp = dict(pot=[0, 0], turns=0, flags=2, stream_pos=len(s.words), hash=board_hash([0, 0, 1, 1], [1, 1, 5, 3]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_cards_and_income():
+    """CARDS catch-up with a set: cash decision draw, random set, +2 on owned card territories, progression value,
+    then PLACEMENT income = max(n/3, 3) + owned continents, one attack, card deal, step limit after the turn."""
+    m, r = line4(), Rules(use_cards=True, transfer_cards=True, max_player_turns=1)
+    # hand: cards of territories 0, 3 and a wildcard (symbols 0, 0, wild) -> exactly one triple, a set
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 1, 30, 9], currentPlayer=0, currentPhase=PHASE_CARDS,
+                      playerNumberOfCards=[0, 0], cardProgressionPos=3, hand=[0, 3, CARD_WILD], deck=[1, 2, CARD_WILD])
+    al, dl, inv = first_row(13, 30)
+    s = Script()
+    s.double(0.25)                 # SimRandom.cardsPhase: 3 cards, r < 0.5 -> cash
+    s.int(1, 0)                    # Card.getRandomSet: one valid triple
+    # cashCards: value(pos 3) = 8 for "4, 6, 8, 10, 15, 20..."; territory 0 is owned -> +2; territory 3 is not
+    #   armies [3, 1, 30, 9], placeable 8, deck [1, 2, W, 0, 3, W]
+    # PLACEMENT: income = max(2 / 3, 3) + bonus of continent 0 (owned: 2) = 5 -> placeable 13
+    s.int(13, 12).int(1, 0)        # place all 13 on the only border territory (1): armies [3, 14, 30, 9]
+    s.int(1, 0).int(1, 0)          # attackers [1] (territory 0 has no enemy neighbour); defenders [2]
+    s.double_k(0)                  # battle 13 v 30 -> first row: the attackers die
+    armies = [3, 14 - al, 30 - dl, 9]
+    owner = [0, 0, 1, 1]
+    assert not inv or armies[2] == 0
+    if inv:                        # conquest: move in 3 + nextInt(avail - 3)
+        avail = armies[1] - 1
+        s.int(avail - 3, 0)
+        armies[2] = 3; armies[1] -= 3; owner[2] = 0
+        # attackers list: [1] stays if armies > 1, territory 2 appended (3 > 1): continue until nothing can attack
+        raise AssertionError("scenario expects the most likely 13 v 30 row to be a defeat of the attacker")
+    # attacker wiped out to 1 army: list empty; no conquest -> no card dealt; FORTIFICATION -> player 1, step limit
+    exp = dict(pot=[0, 0], turns=0, flags=2, stream_pos=len(s.words), hash=board_hash(owner, armies))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+ALL = [scenario_sweep, scenario_catchup_execute_keeps_owner, scenario_cards_and_income]
+
+
+def check(games_row, exp, n_players):
+    assert [int(x) for x in games_row["player_out_on_turn"][:n_players]] == exp["pot"]
+    assert int(games_row["sim_turn_count"]) == exp["turns"]
+    assert int(games_row["flags"]) == exp["flags"]
+    assert int(games_row["stream_pos"]) == exp["stream_pos"]
+    assert int(games_row["board_hash"]) == exp["hash"]

@@ -1,0 +1,130 @@
+"""The C-ABI library loads and exports what include/orx.h declares; host-side mirrors of the record layout.
+No compute calls here (there is no GPU on the CPU test box)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oponn_b200 import build as orx_build
+from oponn_b200 import engine
+from oponn_b200.maps import classic42, synth200
+from oponn_b200.state import (CARD_WILD, GAME_RESULT_DTYPE, LEAF_RESULT_DTYPE, PHASE_ATTACK, ATTACK_EXECUTE, BoardState, Rules,
+                              leaf_layout, pack_leaves)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    orx_build.build()
+    return engine.load_library()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "orx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(orx_[a-z_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_functions() == sorted(engine.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", engine.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (orx_[a-z_]+)", out))
+    assert set(header_functions()) <= exported
+    # plain C ABI: no C++ mangled orx entry points leak out as the interface
+    assert not [s for s in exported if s.startswith("_Z")]
+
+
+def test_library_is_cuda_not_a_cpu_build():
+    """the product contains sm_100a device code and no oracle symbols"""
+    out = subprocess.run(["cuobjdump", "-lelf", engine.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    syms = subprocess.run(["nm", "-D", engine.lib_path()], capture_output=True, text=True).stdout
+    assert "orc_" not in syms
+
+
+def test_engine_fails_loudly_without_a_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.OrxError) as e:
+        engine.RolloutEngine(classic42(6), Rules())
+    assert e.value.code == engine.ORX_E_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_missing_library_is_an_import_error(monkeypatch, tmp_path):
+    monkeypatch.setenv("ORX_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(engine, "_lib", None)
+    with pytest.raises(ImportError):
+        engine.load_library()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "oponn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in text and "oponn_oracle" not in text and "liboponn_oracle" not in text, f
+
+
+def test_struct_sizes_match_the_header():
+    assert GAME_RESULT_DTYPE.itemsize == 48 and LEAF_RESULT_DTYPE.itemsize == 160
+    # compile a probe against the real header
+    probe = r'''
+    #include <stdio.h>
+    #include "orx.h"
+    int main(void) { OrxLeafLayout l = orx_leaf_layout(42, 6), m = orx_leaf_layout(200, 8);
+      printf("%zu %zu %zu %d %d %d %d %d %d\n", sizeof(OrxLeafHeader), sizeof(OrxGameResult), sizeof(OrxLeafResult),
+             l.off_owner, l.off_armies, l.off_ncards, l.off_cards, l.stride, m.stride); return 0; }
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "p.c"), "w").write(probe)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "p"), os.path.join(td, "p.c")])
+        vals = [int(x) for x in subprocess.check_output([os.path.join(td, "p")]).split()]
+    L, M = leaf_layout(42, 6), leaf_layout(200, 8)
+    assert vals == [32, 48, 160, L.off_owner, L.off_armies, L.off_ncards, L.off_cards, L.stride, M.stride]
+
+
+def test_leaf_pack_round_trip():
+    m = classic42(6)
+    rng = np.random.default_rng(0)
+    bs = BoardState(owner=[int(x) for x in rng.integers(0, 6, 42)], armies=[int(x) for x in rng.integers(1, 99, 42)],
+                    currentPlayer=3, currentPhase=PHASE_ATTACK, turnCount=17, playerNumberOfCards=[1, 2, 3, 0, 4, 5],
+                    numberOfPlaceableArmies=12, hasInvadedACountry=True, attackState=ATTACK_EXECUTE, attackingCC=5, defendingCC=9,
+                    defendingPlayer=2, attackUntilDead=False, cardProgressionPos=7, hand=[3, CARD_WILD, 40])
+    buf = bs.pack(m)
+    back = BoardState.unpack(m, buf)
+    assert back.pack(m).tobytes() == buf.tobytes()
+    assert back.hand == [3, CARD_WILD, 40] and len(back.deck) == 41 and back.deck.count(CARD_WILD) == 1
+    assert pack_leaves(m, [bs, back]).shape == (2, leaf_layout(42, 6).stride)
+
+
+def test_maps_are_well_formed():
+    for m in (classic42(6), synth200()):
+        n = m.n_territories
+        for t, nb in enumerate(m.adjacency):
+            assert len(set(nb)) == len(nb)
+            for x in nb:
+                assert t in m.adjacency[x]           # undirected
+        # connected
+        seen, todo = {0}, [0]
+        while todo:
+            for x in m.adjacency[todo.pop()]:
+                if x not in seen:
+                    seen.add(x); todo.append(x)
+        assert len(seen) == n
+    c = classic42(6)
+    assert (c.n_territories, c.n_continents) == (42, 6)
+    assert [c.continent.count(i) for i in range(6)] == [9, 4, 7, 6, 12, 4]
+    assert sum(len(a) for a in c.adjacency) // 2 == 83
+    s = synth200()
+    assert (s.n_territories, s.n_continents, s.n_players) == (200, 10, 8)
