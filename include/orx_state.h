@@ -129,8 +129,8 @@ typedef struct OrxLeafHeader {
  *   -1 <= attacking_cc, defending_cc < N;  -1 <= defending_player < P;  card_pos >= 0;
  *   |placeable| <= ORX_MAX_ARMIES;  n_hand + n_deck <= N + 2;  every card is a territory code or ORX_CARD_WILD;
  *   every owner is < P (or ORX_OWNER_NONE while phase == COUNTRY_SELECTION);  1 <= armies[t] <= ORX_MAX_ARMIES.
- * A flagged playout (ORX_FLAG_ERROR or ORX_FLAG_STREAM_END) reports only its flags: every other field
- * of its OrxGameResult is zero. */
+ * A flagged playout (ORX_FLAG_ERROR or ORX_FLAG_STREAM_END) reports only its first fault -- exactly one of the
+ * two bits -- and every other field of its OrxGameResult is zero. */
 typedef struct OrxLeafLayout {
     int32_t off_owner;    /* uint8  owner[N]    : 0..P-1, ORX_OWNER_NONE            */
     int32_t off_armies;   /* int32  armies[N]                                       */

@@ -473,6 +473,13 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar)
     unsigned long long blocks = warps / (ORX_BLOCK_THREADS / 32);
     if (need < blocks) blocks = need;
     if (blocks == 0) blocks = 1;
+    // the opt-in shared-memory size is per function, not per context: re-assert it for this context's map
+    {
+        int dummy;
+        cudaError_t e = c->nwt == 2 ? (replay ? configure_kernel<2, true>(c->smem_bytes, &dummy) : configure_kernel<2, false>(c->smem_bytes, &dummy))
+                                    : (replay ? configure_kernel<8, true>(c->smem_bytes, &dummy) : configure_kernel<8, false>(c->smem_bytes, &dummy));
+        if (e != cudaSuccess) return set_err(ORX_E_CUDA, "configure_kernel: %s", cudaGetErrorString(e));
+    }
     CK(cudaEventRecord(c->ev0, c->stream));
     dim3 grid((unsigned)blocks), block(ORX_BLOCK_THREADS);
     if (c->nwt == 2) {

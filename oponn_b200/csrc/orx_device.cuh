@@ -147,7 +147,7 @@ struct Stream {
     {
         if (REPLAY) {
             uint32_t i = base++;
-            if (i >= n_words) { flags |= ORX_FLAG_STREAM_END; return 0u; }
+            if (i >= n_words) { if (!flags) flags |= ORX_FLAG_STREAM_END; return 0u; }  // only the first fault is recorded
             return __ldg(words + i);
         }
         if (wi == 128u) refill();

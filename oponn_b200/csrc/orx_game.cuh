@@ -705,7 +705,7 @@ struct Game {
     {
         uint32_t flags = s.flags;
         bool dead = (flags & (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END)) != 0u;
-        if (dead) flags &= (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END);
+        if (dead) flags = (flags & ORX_FLAG_STREAM_END) ? ORX_FLAG_STREAM_END : ORX_FLAG_ERROR;  // the first fault only
         uint32_t hsum = 0;
         if (!dead) {
 #pragma unroll

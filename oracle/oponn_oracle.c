@@ -87,7 +87,7 @@ static uint32_t stream_word(Stream *s)
 {
     uint32_t i = s->pos++;
     if (s->inj) {
-        if (i >= s->inj_len) { *s->flags |= ORX_FLAG_STREAM_END; return 0; }
+        if (i >= s->inj_len) { if (!*s->flags) *s->flags |= ORX_FLAG_STREAM_END; return 0; } /* only the first fault is recorded */
         return s->inj[i];
     }
     int64_t blk = i >> 7;
@@ -1325,8 +1325,9 @@ static void run_one(Board *b, const OrcCtx *c, const uint8_t *leaf, uint64_t see
     if (!b->flags) simulate(b);
     memset(out, 0, sizeof *out);
     if (b->flags & (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END)) {
-        /* a flagged playout reports only its flags (include/orx_state.h) */
-        out->flags = b->flags & (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END);
+        /* a flagged playout reports only its first fault (include/orx_state.h): the stream ending can only be
+         * recorded while no other flag is up, and whatever it provokes afterwards is not reported */
+        out->flags = (b->flags & ORX_FLAG_STREAM_END) ? ORX_FLAG_STREAM_END : ORX_FLAG_ERROR;
     } else {
         for (int p = 0; p < b->P; p++) out->player_out_on_turn[p] = b->playerOutOnTurn[p];
         out->sim_turn_count = b->simTurnCount;

@@ -42,6 +42,8 @@ def phase_zoo(m, base: np.ndarray = None, seed: int = 3):
                  playerNumberOfCards=list(bs0.playerNumberOfCards), cardProgressionPos=bs0.cardProgressionPos,
                  hand=list(bs0.hand), deck=None if bs0.deck is None else list(bs0.deck))
         d.update(kw)
+        if "hand" in kw and "deck" not in kw:
+            d["deck"] = None                       # the rest of the cards, in code order
         b = BoardState(**d)
         out.append(b); names.append(name)
         return b

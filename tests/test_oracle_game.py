@@ -90,11 +90,12 @@ def test_step_limit_and_stream_end(classic, mid_leaf):
     assert np.all(games["flags"] == FLAG_STREAM_END) and np.all(games["board_hash"] == 0)
 
 
-def test_every_phase_plays_to_the_end(oracle, classic):
+@pytest.mark.parametrize("from_mid_game", [False, True])
+def test_every_phase_plays_to_the_end(oracle, classic, mid_leaf, from_mid_game):
     from leafzoo import phase_zoo
-    leaves, names = phase_zoo(classic)
-    _, games = oracle.rollout_batch(leaves, 8, 11, per_game=True, threads=8)
-    games = games.reshape(len(names), 8)
+    leaves, names = phase_zoo(classic, mid_leaf if from_mid_game else None)
+    _, games = oracle.rollout_batch(leaves, 4, 11, per_game=True, threads=8)
+    games = games.reshape(len(names), 4)
     for i, name in enumerate(names):
         assert np.all(games[i]["flags"] == 0), name
         assert np.all((games[i]["player_out_on_turn"][:, :6] == -1).sum(axis=1) == 1), name
