@@ -421,6 +421,10 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
         CKC((configure_kernel<8, false>(c->smem_bytes, &c->blocks_per_sm[0])));
         CKC((configure_kernel<8, true>(c->smem_bytes, &c->blocks_per_sm[1])));
     }
+    if (const char *lim = getenv("ORX_BLOCKS_PER_SM")) {  // tuning knob: cap the resident blocks per SM
+        int v = atoi(lim);
+        if (v >= 1) for (int k = 0; k < 2; k++) if (c->blocks_per_sm[k] > v) c->blocks_per_sm[k] = v;
+    }
     if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) { set_err(ORX_E_CUDA, "rollout kernel does not fit on an SM"); orx_destroy(c); return ORX_E_CUDA; }
     CKC(cudaStreamSynchronize(c->stream));
 #undef CKC

@@ -21,7 +21,7 @@
 
 #define ORX_FULL 0xFFFFFFFFu
 #define ORX_TABLE_LIMIT 100
-#define ORX_MAGIC_N 1024
+#define ORX_MAGIC_N 4096
 
 namespace orx {
 
@@ -274,6 +274,8 @@ __device__ __forceinline__ double next_gaussian(Stream<REPLAY> &s)
     } while (q >= 1.0 || q == 0.0);
     double second;
     double first = gaussian_from_pair(v1, v2, q, &second);
+    // every lane computed the same pair; the shuffles only make that visible to the PTX uniformity pass
+    first = __shfl_sync(ORX_FULL, first, 0); second = __shfl_sync(ORX_FULL, second, 0);
     __syncwarp();
     if (lane_id() == 0) {
         sts32(s.hdr + 4 * WH_GAUSS_LO, (uint32_t)__double2loint(second)); sts32(s.hdr + 4 * WH_GAUSS_HI, (uint32_t)__double2hiint(second));

@@ -337,6 +337,45 @@ struct Game {
         attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
     }
 
+    // possibleAttackers (SimRandom.java:61,88-140) as a register-resident ordered list when it fits 64 entries
+    // (NWT <= 2: lane l holds entries l and l + 32); shared memory otherwise.  get / remove(index) / add(tail).
+    struct AttackerList {
+        int lo, hi, n;
+    };
+    __device__ __forceinline__ int alist_get(const AttackerList &L, int i) const
+    {
+        if (NWT <= 2) {
+            int a = __shfl_sync(ORX_FULL, L.lo, i & 31), b = __shfl_sync(ORX_FULL, L.hi, i & 31);
+            return i < 32 ? a : b;
+        }
+        return (int)lds8(a_alist + (uint32_t)i);
+    }
+    __device__ __forceinline__ void alist_remove(AttackerList &L, int i)
+    {
+        if (NWT <= 2) {
+            int dlo = __shfl_down_sync(ORX_FULL, L.lo, 1);
+            if (L.n > 32) {
+                int h0 = __shfl_sync(ORX_FULL, L.hi, 0), dhi = __shfl_down_sync(ORX_FULL, L.hi, 1);
+                if (lane == 31) dlo = h0;
+                if (lane + 32 >= i) L.hi = dhi;
+            }
+            if (lane >= i) L.lo = dlo;
+        } else {
+            bytes_remove_at(a_alist, L.n, i);
+        }
+        L.n--;
+    }
+    __device__ __forceinline__ void alist_add(AttackerList &L, int t)
+    {
+        if (NWT <= 2) {
+            if (lane == L.n) L.lo = t;
+            if (lane + 32 == L.n) L.hi = t;
+        } else {
+            __syncwarp(); if (lane == 0) sts8(a_alist + (uint32_t)L.n, (uint32_t)t); __syncwarp();
+        }
+        L.n++;
+    }
+
     // SimRandom.attackPhase (SimRandom.java:58-141) with SimulationBoard.attack (:713-744) inlined
     __device__ __forceinline__ void agent_attack_phase()
     {
@@ -344,65 +383,63 @@ struct Game {
         owned_mask(cp, mine);
         border_mask(mine, true, att);
         // possibleAttackers: code order
-        int nAtt = 0;
+        AttackerList L;
+        L.n = 0; L.lo = 0; L.hi = 0;
         __syncwarp();
 #pragma unroll
         for (int w = 0; w < NWT; w++) {
-            if ((att[w] >> lane) & 1u) sts8(a_alist + (uint32_t)(nAtt + __popc(att[w] & lanemask_lt())), (uint32_t)(w * 32 + lane));
-            nAtt += __popc(att[w]);
+            if ((att[w] >> lane) & 1u) sts8(a_alist + (uint32_t)(L.n + __popc(att[w] & lanemask_lt())), (uint32_t)(w * 32 + lane));
+            L.n += __popc(att[w]);
         }
         __syncwarp();
+        if (NWT <= 2) { L.lo = (int)lds8(a_alist + (uint32_t)lane); L.hi = (int)lds8(a_alist + 32u + (uint32_t)lane); }
         attackUntilDead = 1;
-        uint32_t guard = 0;
-        while (nAtt > 0 && !s.flags) {
-            if (++guard > (1u << 24)) { fail(); break; }
-            int ai = s.next_int(nAtt);
-            int A = (int)lds8(a_alist + (uint32_t)ai);
+        const int me = cp;
+        while (L.n > 0 && !s.flags) {
+            int ai = s.next_int(L.n);
+            int A = alist_get(L, ai);
             // possibleDefenders: non-owned out-neighbours in getAdjoiningList() order
             int dg = deg(A);
             int nb = 0;
             bool enemy = false;
-            if (lane < dg) { nb = adj(A, lane); enemy = owner(nb) != cp; }
+            if (lane < dg) { nb = adj(A, lane); enemy = owner(nb) != me; }
             uint32_t dmask = __ballot_sync(ORX_FULL, enemy);
-            int nDef = __popc(dmask);
-            if (nDef == 0) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; continue; }
-            int D = from_lane(nb, nth_bit(dmask, s.next_int(nDef)));
+            if (dmask == 0u) { alist_remove(L, ai); continue; }
+            int D = from_lane(nb, nth_bit(dmask, s.next_int(__popc(dmask))));
             // SimulationBoard.attack: setupAttack, executeAttack, finishAttack
             saddr pA = a_arm + 4u * (uint32_t)A, pD = a_arm + 4u * (uint32_t)D;
             int aArm = (int)lds32(pA), dArm = (int)lds32(pD);
             int al, dl;
             simulate_battle(dm, s, aArm - 1, dArm, al, dl);
-            if (s.flags) return;
             aArm -= al; dArm -= dl;
             if (dArm == 0) {
                 // setupInvasion (:797-812)
                 int dp = owner(D);
-                if (lane == cp) pc++;
+                if (lane == me) pc++;
                 if (lane == dp) pc--;
                 // SimRandom.moveArmiesIn (SimRandom.java:144-155) + executeInvasion (:814-825)
                 int available = aArm - 1;
                 if (available == 0) { fail(); return; }
-                int mn = available < 3 ? available : 3;
-                int inv = mn + (mn == available ? 0 : s.next_int(available - mn));  // already within [min(avail,3), avail]
+                int inv = available;
+                if (available > 3) inv = 3 + s.next_int(available - 3);  // already within [min(avail,3), avail]
                 aArm -= inv; dArm = inv;
                 __syncwarp();
-                if (lane == 0) { sts32(pA, (uint32_t)aArm); sts32(pD, (uint32_t)dArm); sts8(a_own + (uint32_t)D, (uint32_t)cp); }
+                if (lane == 0) { sts32(pA, (uint32_t)aArm); sts32(pD, (uint32_t)dArm); sts8(a_own + (uint32_t)D, (uint32_t)me); }
                 __syncwarp();
                 // finishInvasion (:827-841)
-                if (from_lane(pc, dp) == 0) { player_defeated(dp, cp); if (s.flags) return; }
+                if (from_lane(pc, dp) == 0) player_defeated(dp, me);
                 hasInvaded = 1;
                 // result == DEFENDERS_DESTROYED (SimRandom.java:127-137)
-                if (aArm == 1) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; }
+                if (aArm == 1) alist_remove(L, ai);
                 if (dArm > 1) {
-                    if (nAtt >= dm.cap) { fail(); return; }
-                    __syncwarp(); if (lane == 0) sts8(a_alist + (uint32_t)nAtt, (uint32_t)D); __syncwarp();
-                    nAtt++;
+                    if (L.n >= dm.cap) { fail(); return; }
+                    alist_add(L, D);
                 }
             } else {
                 __syncwarp();
                 if (lane == 0) { sts32(pA, (uint32_t)aArm); sts32(pD, (uint32_t)dArm); }
                 __syncwarp();
-                if (aArm == 1) { bytes_remove_at(a_alist, nAtt, ai); nAtt--; }  // ATTACKERS_DESTROYED
+                if (aArm == 1) alist_remove(L, ai);  // ATTACKERS_DESTROYED
             }
         }
         attackState = ORX_ATTACK_START;
@@ -746,11 +783,14 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
         for (int i = threadIdx.x; i < dm.blob_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const int wid = threadIdx.x >> 5;
+    // warp index through a shuffle: a warp-uniform value the PTX uniformity pass can see (ptx_uniform.py)
+    const int wid = __shfl_sync(ORX_FULL, (int)(threadIdx.x >> 5), 0);
     uint8_t *slice = smem + dm.blob_bytes + wid * dm.w_bytes;
 
     Game<NWT, REPLAY> g(dm);
-    const saddr sbase = to_saddr(smem), wbase = to_saddr(slice);
+    // pinned in registers: without the barrier ptxas re-derives the shared window base inside the hot loops
+    saddr sbase = to_saddr(smem), wbase = to_saddr(slice);
+    asm volatile("" : "+r"(sbase), "+r"(wbase));
     g.s_adj = sbase + (uint32_t)dm.adj_off; g.s_deg = sbase + (uint32_t)dm.deg_off; g.s_sym = sbase + (uint32_t)dm.sym_off;
     g.s_nbr = sbase + (uint32_t)dm.nbr_off; g.s_cont = sbase + (uint32_t)dm.cont_off; g.s_bonus = sbase + (uint32_t)dm.bonus_off;
     g.lane = lane_id();

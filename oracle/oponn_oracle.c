@@ -942,9 +942,7 @@ static void agent_attackPhase(Board *b)
                 if (b->owner[b->adj[e]] != ID) { possibleAttackers[nAtt++] = c; break; }
             }
     }
-    uint32_t guard = 0;
     while (nAtt > 0 && !b->flags) {
-        if (++guard > (1u << 24)) { FAIL(b); break; } /* engine guard against a runaway phase */
         int attackerIndex = jr_next_int(&b->rng, nAtt);
         int attacker = possibleAttackers[attackerIndex];
         nDef = 0;
