@@ -17,6 +17,10 @@ SOURCES = [os.path.join(CSRC, "orx_api.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("orx_device.cuh", "orx_game.cuh")] + \
     [os.path.join(INCLUDE, f) for f in ("orx.h", "orx_state.h")] + [os.path.join(HERE, "ptx_uniform.py")]
 
+#: resident blocks per SM that ptxas budgets registers for (9 x 128 threads -> 56 registers).  The source carries a
+#: loose bound (ORX_MIN_BLOCKS 5) for the front end; see ptx_uniform.transform.
+PTXAS_MIN_BLOCKS = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS", "9"))
+
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -69,7 +73,7 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
         script.append(st)
         if "/cicc" in st.split(" ")[0] or st.lstrip().startswith('"$CICC_PATH/cicc"'):
             ptx = st.rsplit('-o "', 1)[1].rstrip('" ')
-            script.append(f'"{sys.executable}" "{os.path.join(HERE, "ptx_uniform.py")}" "{ptx}" "{ptx}"')
+            script.append(f'"{sys.executable}" "{os.path.join(HERE, "ptx_uniform.py")}" "{ptx}" "{ptx}" {PTXAS_MIN_BLOCKS}')
     sh = os.path.join(keep, "build.sh")
     open(sh, "w").write("\n".join(script) + "\n")
     r = subprocess.run(["bash", sh], capture_output=True, text=True, cwd=os.path.join(HERE, ".."))

@@ -13,7 +13,7 @@
 
 #define ORX_BLOCK_THREADS 128
 #ifndef ORX_MIN_BLOCKS
-#define ORX_MIN_BLOCKS 5   /* 20 warps/SM, up to 96 registers: more resident warps bought nothing (profiles/r1b) */
+#define ORX_MIN_BLOCKS 5   /* bound seen by the front end; ptxas gets the tight one (build.py) */
 #endif
 
 #include "../../include/orx.h"

@@ -73,7 +73,30 @@ def parse(lines: List[str], lo: int, hi: int):
         if m:
             labels[m.group(1)] = idx
             continue
-        if s in ("{", "}") or not s.endswith(";"):
+        if s in ("{", "}"):
+            continue
+        if s.startswith("{") and s.endswith("}") and ";" in s:
+            # an inline-asm block written on one line: "{ .reg .pred q; setp ...; @q st ...; }".  Registers declared
+            # inside are private names; treat every statement separately, conservatively (any %-register counts).
+            for stmt in s[1:-1].split(";"):
+                stmt = stmt.strip()
+                if not stmt or stmt.startswith("."):
+                    continue
+                i = Ins()
+                i.idx, i.guard, i.op, i.text, i.target, i.addr = idx, None, "asmblock", s, None, []
+                regs = REG.findall(stmt)
+                g = re.match(r"^@!?(\S+)\s+(.*)$", stmt)
+                body2 = g.group(2) if g else stmt
+                opn = body2.split(None, 1)[0]
+                if any(opn.startswith(p_) for p_ in NO_DEST):
+                    i.dests, i.srcs = [], regs
+                else:
+                    ops2 = split_operands(body2.split(None, 1)[1] if " " in body2 else "")
+                    i.dests = REG.findall(ops2[0]) if ops2 else []
+                    i.srcs = regs          # every register of the block may feed the result (private predicates)
+                ins.append(i)
+            continue
+        if not s.endswith(";"):
             continue
         body = s[:-1].strip()
         guard = None
@@ -304,9 +327,20 @@ def analyse(lines: List[str], lo: int, hi: int) -> Tuple[List[int], int]:
         div_blocks |= new_div
 
 
-def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False) -> str:
+def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False, min_blocks: int = 0) -> str:
+    """``min_blocks`` > 0 also rewrites ``.minnctapersm`` of the matching kernels: the front end is compiled with a
+    loose ``__launch_bounds__`` (it produces markedly worse code under a tight register budget: 105k vs 158k
+    playouts/s measured) and only ptxas is given the tight one."""
     lines = ptx.split("\n")
     stats = []
+    if min_blocks > 0:
+        cur = ""
+        for n, ln in enumerate(lines):
+            m = re.match(r"^(?:\.visible\s+|\.weak\s+)?\.(entry|func)\s+(?:\([^)]*\)\s*)?([_A-Za-z0-9$]+)", ln)
+            if m:
+                cur = m.group(2)
+            if only in cur and ln.startswith(".minnctapersm"):
+                lines[n] = f".minnctapersm {min_blocks}"
     for lo, hi, name in split_functions(lines):
         if only not in name:
             continue
@@ -322,5 +356,6 @@ def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False) -> 
 
 if __name__ == "__main__":
     src, dst = sys.argv[1], sys.argv[2]
-    text = transform(open(src).read(), verbose=True)   # read fully before (possibly) overwriting in place
+    mb = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    text = transform(open(src).read(), verbose=True, min_blocks=mb)   # read fully before (possibly) overwriting in place
     open(dst, "w").write(text)
