@@ -247,59 +247,69 @@ def analyse(lines: List[str], lo: int, hi: int) -> Tuple[List[int], int]:
 
     forced: Set[int] = set()
     div_blocks: Set[int] = set()
+    # registers as bit positions: the variant sets of the data-flow are Python ints
+    regno: Dict[str, int] = {}
+
+    def bits(regs) -> int:
+        m = 0
+        for r in regs:
+            k = regno.get(r)
+            if k is None:
+                k = regno[r] = len(regno)
+            m |= 1 << k
+        return m
+
+    KIND_SEED, KIND_UNI, KIND_SHFL, KIND_DATA = 0, 1, 2, 3
+    pre = []   # per instruction: (kind, dest mask, source mask, guard mask, is conditional branch)
+    for i in ins:
+        op, t = i.op, i.text
+        if any(s_ in t for s_ in VARIANT_SREGS) or op.startswith("atom.") or op.startswith("activemask") or \
+                (op.startswith("ld.param") and "retval" in t) or (op.startswith("shfl.sync") and not op.startswith("shfl.sync.idx")):
+            kind, src = KIND_SEED, 0
+        elif op.startswith("vote.sync") or op.startswith("redux.sync"):
+            kind, src = KIND_UNI, 0
+        elif op.startswith("shfl.sync.idx"):
+            ops = split_operands(t[:-1].split(None, 1)[1] if i.guard is None else t[:-1].split(None, 2)[2])
+            kind, src = KIND_SHFL, bits([r for o in ops[2:] for r in REG.findall(o)])   # lane, clamp, membermask
+        else:
+            kind, src = KIND_DATA, bits(i.srcs)
+        pre.append((kind, bits(i.dests), src, bits([i.guard]) if i.guard else 0, i.op.startswith("bra") and i.guard is not None))
     while True:
         # ---- forward data-flow: IN[b] = union OUT[pred]
-        IN = [set() for _ in range(nb)]
+        IN = [0] * nb
         OUT = [None] * nb
-        work = list(range(nb))
+        from collections import deque
+        work = deque(range(nb))
         inwork = [True] * nb
         guard_var: Dict[int, bool] = {}
         while work:
-            b = work.pop(0)
+            b = work.popleft()
             inwork[b] = False
-            cur = set(IN[b])
+            cur = IN[b]
             st, en = blocks[b]
             fb = b in forced
             for n in range(st, en):
-                i = ins[n]
-                if i.op.startswith("bra") and i.guard is not None:
-                    guard_var[n] = i.guard in cur
-                if not i.dests:
+                kind, dmask, smask, gmask, isbr = pre[n]
+                if isbr:
+                    guard_var[n] = bool(cur & gmask)
+                if not dmask:
                     continue
-                op, t = i.op, i.text
-                if fb or any(s_ in t for s_ in VARIANT_SREGS) or op.startswith("atom.") or op.startswith("activemask") or \
-                        (op.startswith("ld.param") and "retval" in t):
-                    v = True
-                elif op.startswith("vote.sync") or op.startswith("redux.sync"):
-                    v = False
-                elif op.startswith("shfl.sync.idx"):
-                    ops = split_operands(t[:-1].split(None, 1)[1] if i.guard is None else t[:-1].split(None, 2)[2])
-                    v = any(r in cur for o in ops[2:] for r in REG.findall(o))
-                elif op.startswith("shfl.sync"):
-                    v = True
-                else:
-                    v = any(r in cur for r in i.srcs)
-                if i.guard is not None and i.guard in cur:
-                    v = True
+                v = fb or kind == KIND_SEED or (kind >= KIND_SHFL and bool(cur & smask)) or bool(cur & gmask)
                 if TRACE is not None and v:
-                    c = "forced" if fb else next((r for r in i.srcs if r in cur), None) or (i.guard if i.guard in cur else "seed")
+                    i = ins[n]
+                    c = "forced" if fb else next((r for r in i.srcs if (cur >> regno[r]) & 1), None) or \
+                        (i.guard if gmask and cur & gmask else "seed")
                     TRACE.setdefault(n, (c, i.text, i.idx))
-                if i.guard is not None and not v:
-                    # a predicated write keeps the old value in the lanes where the guard is false: with a uniform
-                    # guard the result is uniform only if the old value was
-                    for d in i.dests:
-                        pass  # leave membership unchanged
-                    continue
-                for d in i.dests:
-                    if v:
-                        cur.add(d)
-                    else:
-                        cur.discard(d)
+                if v:
+                    cur |= dmask
+                elif not gmask:
+                    cur &= ~dmask
+                # a predicated write with a uniform guard keeps the old value where the guard is false: unchanged
             if OUT[b] is None or cur != OUT[b]:
                 OUT[b] = cur
                 for t_ in succ[b]:
-                    if t_ != EXIT and not (OUT[b] <= IN[t_]):
-                        IN[t_] |= OUT[b]
+                    if t_ != EXIT and (cur & ~IN[t_]):
+                        IN[t_] |= cur
                         if not inwork[t_]:
                             work.append(t_); inwork[t_] = True
         new_div = {block_of[n] for n, v in guard_var.items() if v}
@@ -311,18 +321,6 @@ def analyse(lines: List[str], lo: int, hi: int) -> Tuple[List[int], int]:
             if DEBUG:
                 st, en = blocks[b]
                 print(f"  divergent branch @line {ins[en-1].idx}: {ins[en-1].text}  region {len(r)} blocks", file=sys.stderr)
-                if len(r) > 100 and TRACE is not None:
-                    reg, cur = ins[en - 1].guard, en - 1
-                    for _ in range(40):
-                        d = next((n for n in range(cur - 1, -1, -1) if reg in ins[n].dests and n in TRACE), None)
-                        if d is None:
-                            print("   no def for", reg, file=sys.stderr); break
-                        c, t, idx = TRACE[d]
-                        print("   ", idx + 1, t, "<=", c, file=sys.stderr)
-                        if c in ("forced", "seed"):
-                            break
-                        reg, cur = c, d
-                    raise SystemExit(0)
             forced |= r
         div_blocks |= new_div
 
