@@ -41,6 +41,16 @@ def load_workload() -> dict:
     return json.load(open(os.path.join(ROOT, "tests", "golden", "workload_classic42_mid_s1.json")))
 
 
+def load_traffic(playouts: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch, from the committed ncu capture of the same
+    launch size (profiles/rollout_traffic.json); None when the capture was taken at another size."""
+    p = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["traffic_bytes_per_launch"] if d.get("playouts_per_launch") == playouts else None
+
+
 def measured_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,7 +270,7 @@ def run_ours(args):
                          "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']} MHz "
                                         f"({peaks['_source']} clock, MEASURED_PEAKS.json)",
                          "algorithmic_int_ops_per_playout": A, "kernel_ms_avg": k_avg_ms,
-                         "traffic": None,
+                         "traffic": load_traffic(P),
                          "hbm_side_check": {"algorithmic_bytes_per_launch": alg_bytes,
                                             "achieved_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9,
                                             "peak_gbs": peaks["hbm_gbs"]}},
