@@ -120,7 +120,8 @@ typedef struct OrxLeafHeader {
     uint8_t n_hand;            /* |CardManager.inHand|: the real hand, handed to
                                   whoever is current_player (SimulationBoard.java:215-218) */
     uint8_t n_deck;            /* |CardManager.notInHand|: the unseen deck, in list order */
-    uint8_t reserved[10];
+    uint8_t reserved[10];      /* [0]: tree-only, Attack.attackUntilDead of a pending (EXECUTE) attack as the
+                                  exploration board holds it (orx_tree.h); rollouts ignore all ten bytes */
 } OrxLeafHeader;
 
 /* Leaf validity (engine contract; the reference would throw, loop or index out of bounds on

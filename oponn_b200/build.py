@@ -13,16 +13,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "liborx.so")
-SOURCES = [os.path.join(CSRC, "orx_api.cu")]
+SOURCES = [os.path.join(CSRC, "orx_api.cu"), os.path.join(CSRC, "orx_tree.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("orx_device.cuh", "orx_game.cuh")] + \
-    [os.path.join(INCLUDE, f) for f in ("orx.h", "orx_state.h")] + [os.path.join(HERE, "ptx_uniform.py")]
+    [os.path.join(INCLUDE, f) for f in ("orx.h", "orx_state.h", "orx_tree.h")] + [os.path.join(HERE, "ptx_uniform.py")]
 
 #: resident blocks per SM that ptxas budgets registers for (9 x 128 threads -> 56 registers).  The source carries a
 #: loose bound (ORX_MIN_BLOCKS 5) for the front end; see ptx_uniform.transform.
 PTXAS_MIN_BLOCKS = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS", "9"))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]
 
 
 def nvcc() -> str:

@@ -22,22 +22,25 @@ def lib():
     return engine.load_library()
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "orx.h")).read()
+def header_functions(name="orx.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"static inline[^{]*\{[^}]*\}", "", src)
     return sorted(set(re.findall(r"\b(orx_[a-z_]+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
+    from oponn_b200 import tree
     assert header_functions() == sorted(engine.EXPORTS)
+    assert header_functions("orx_tree.h") == sorted(tree.TREE_EXPORTS)
 
 
 def test_library_exports_every_declared_symbol(lib):
-    for name in header_functions():
+    for name in header_functions() + header_functions("orx_tree.h"):
         assert hasattr(lib, name), name
     out = subprocess.run(["nm", "-D", "--defined-only", engine.lib_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (orx_[a-z_]+)", out))
-    assert set(header_functions()) <= exported
+    assert set(header_functions()) | set(header_functions("orx_tree.h")) <= exported
     # plain C ABI: no C++ mangled orx entry points leak out as the interface
     assert not [s for s in exported if s.startswith("_Z")]
 
