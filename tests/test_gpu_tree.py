@@ -46,7 +46,7 @@ def test_batched_agrees_with_one_leaf_at_a_time(engine, classic, mid_leaf):
     est = {}
     for lif in (1, 512):
         tree = SearchTree(classic, Rules(), TreeOptions(agent_id=0, playouts_per_leaf=8, leaves_in_flight=lif, seed=11), engine)
-        ch, st = tree.search(bs, 1500)
+        ch, st = tree.search(bs, 400)
         tree.close()
         n = int(ch["visits"].sum())
         est[lif] = (ch["wins"][:, 0].sum() / n, n, ch)

@@ -45,3 +45,32 @@ def test_shard_covers_everything():
             for (lo, c), (lo2, _) in zip(parts, parts[1:]):
                 assert lo + c == lo2
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def _merge_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oponn_b200.tree import ROOT_CHILD_DTYPE, merge_root_children
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    ch = np.zeros(5, dtype=ROOT_CHILD_DTYPE)
+    ch["move"]["type"] = 4; ch["move"]["a"] = np.arange(5)
+    for f in ("wins", "losses", "win_len_sum", "loss_len_sum"):
+        ch[f] = rng.integers(0, 1000, size=ch[f].shape)
+    ch["visits"] = rng.integers(0, 5000, size=5)
+    np.save(os.path.join(out_dir, f"local{rank}.npy"), ch)
+    np.save(os.path.join(out_dir, f"merged{rank}.npy"), merge_root_children(ch))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_root_parallel_merge(tmp_path):
+    """independent trees merge by summing the integer root statistics with one all-reduce"""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_merge_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    l0, l1 = np.load(tmp_path / "local0.npy"), np.load(tmp_path / "local1.npy")
+    m0, m1 = np.load(tmp_path / "merged0.npy"), np.load(tmp_path / "merged1.npy")
+    assert m0.tobytes() == m1.tobytes()
+    for f in ("visits", "wins", "losses", "win_len_sum", "loss_len_sum"):
+        assert np.array_equal(m0[f], l0[f] + l1[f])
+    assert m0["move"].tobytes() == l0["move"].tobytes()
