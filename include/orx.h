@@ -66,6 +66,14 @@ int orx_rollout_batch_device(OrxCtx *ctx, const void *leaves_dev, int n_leaves, 
                              uint64_t seed, uint64_t first_game,
                              OrxLeafResult *agg_dev, OrxGameResult *games_dev);
 
+/* The same call split in two, on one of two independent in-flight slots (slot 0 or 1, each with its own CUDA
+ * stream): begin copies the leaves and launches, end waits and copies the results back.  Two batches in flight let
+ * the tail of one (a batch ends with its longest game) overlap the bulk of the next: the batched search
+ * (orx_tree.h) alternates slots.  `games` may be NULL in both; a slot must be ended before it is begun again. */
+int orx_rollout_begin(OrxCtx *ctx, int slot, const void *leaves, int n_leaves, int playouts_per_leaf,
+                      uint64_t seed, uint64_t first_game, int want_games);
+int orx_rollout_end(OrxCtx *ctx, int slot, OrxLeafResult *agg, OrxGameResult *games);
+
 /* Replay of injected streams (the "identical injected dice/move stream" harness): game g
  * plays leaf g with the explicit words words[g*words_per_game ...].  HOST buffers. */
 int orx_rollout_replay(OrxCtx *ctx, const void *leaves, int n_games,

@@ -208,6 +208,16 @@ struct OrxCtx {
     void *d_words = nullptr; size_t cap_words = 0;
     bool have_time = false;
     uint64_t launches = 0;
+    // two independent in-flight batches for orx_rollout_begin / orx_rollout_end
+    struct AsyncSlot {
+        cudaStream_t stream = nullptr;
+        unsigned long long *d_ticket = nullptr;
+        void *d_leaves = nullptr; size_t cap_leaves = 0;
+        void *d_agg = nullptr; size_t cap_agg = 0;
+        void *d_games = nullptr; size_t cap_games = 0;
+        int n_leaves = 0, ppl = 0;
+        bool want_games = false, busy = false;
+    } aslot[2];
 };
 
 static int ensure(void **p, size_t *cap, size_t need)
@@ -440,6 +450,10 @@ extern "C" void orx_destroy(OrxCtx *c)
     cudaFree(c->d_blob); cudaFree(c->d_bonus_table); cudaFree(c->d_card_table); cudaFree(c->d_meta);
     cudaFree(c->d_rows); cudaFree(c->d_probs); cudaFree(c->d_ticket);
     cudaFree(c->d_leaves); cudaFree(c->d_agg); cudaFree(c->d_games); cudaFree(c->d_words);
+    for (auto &a : c->aslot) {
+        if (a.stream) { cudaStreamSynchronize(a.stream); cudaStreamDestroy(a.stream); }
+        cudaFree(a.d_ticket); cudaFree(a.d_leaves); cudaFree(a.d_agg); cudaFree(a.d_games);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -468,10 +482,12 @@ extern "C" float orx_last_kernel_ms(OrxCtx *c)
     return ms;
 }
 
-// one launch of the rollout kernel on the context's stream, bracketed by the timing events
-static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar)
+// one launch of the rollout kernel on `stream` (default: the context's stream, bracketed by the timing events)
+static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStream_t stream = nullptr)
 {
-    CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), c->stream));
+    const bool timed = stream == nullptr;
+    if (!stream) stream = c->stream;
+    CK(cudaMemsetAsync(ar.ticket, 0, sizeof(unsigned long long), stream));
     unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[replay] * (ORX_BLOCK_THREADS / 32);
     unsigned long long need = (ar.total + (ORX_BLOCK_THREADS / 32) - 1) / (ORX_BLOCK_THREADS / 32);
     unsigned long long blocks = warps / (ORX_BLOCK_THREADS / 32);
@@ -484,18 +500,17 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar)
                                     : (replay ? configure_kernel<8, true>(c->smem_bytes, &dummy) : configure_kernel<8, false>(c->smem_bytes, &dummy));
         if (e != cudaSuccess) return set_err(ORX_E_CUDA, "configure_kernel: %s", cudaGetErrorString(e));
     }
-    CK(cudaEventRecord(c->ev0, c->stream));
+    if (timed) CK(cudaEventRecord(c->ev0, stream));
     dim3 grid((unsigned)blocks), block(ORX_BLOCK_THREADS);
     if (c->nwt == 2) {
-        if (replay) rollout_kernel<2, true><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
-        else rollout_kernel<2, false><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+        if (replay) rollout_kernel<2, true><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
+        else rollout_kernel<2, false><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
     } else {
-        if (replay) rollout_kernel<8, true><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
-        else rollout_kernel<8, false><<<grid, block, c->smem_bytes, c->stream>>>(c->dm, ar);
+        if (replay) rollout_kernel<8, true><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
+        else rollout_kernel<8, false><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->have_time = true;
+    if (timed) { CK(cudaEventRecord(c->ev1, stream)); c->have_time = true; }
     c->launches++;
     return ORX_OK;
 }
@@ -535,6 +550,49 @@ extern "C" int orx_rollout_batch(OrxCtx *c, const void *leaves, int n_leaves, in
     if (agg) CK(cudaMemcpyAsync(agg, c->d_agg, sizeof(OrxLeafResult) * (size_t)n_leaves, cudaMemcpyDeviceToHost, c->stream));
     if (games) CK(cudaMemcpyAsync(games, c->d_games, sizeof(OrxGameResult) * total, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return ORX_OK;
+}
+
+extern "C" int orx_rollout_begin(OrxCtx *c, int slot, const void *leaves, int n_leaves, int playouts_per_leaf, uint64_t seed,
+                                 uint64_t first_game, int want_games)
+{
+    if (!c || slot < 0 || slot > 1 || !leaves || n_leaves < 1 || playouts_per_leaf < 1) return set_err(ORX_E_INVALID, "bad argument");
+    OrxCtx::AsyncSlot &a = c->aslot[slot];
+    if (a.busy) return set_err(ORX_E_INVALID, "slot still in flight: call orx_rollout_end first");
+    CK(cudaSetDevice(c->device));
+    if (!a.stream) {
+        CK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&a.d_ticket, sizeof(unsigned long long)));
+    }
+    size_t total = (size_t)n_leaves * (size_t)playouts_per_leaf, lbytes = (size_t)n_leaves * (size_t)c->dm.leaf_stride;
+    int rc;
+    if ((rc = ensure(&a.d_leaves, &a.cap_leaves, lbytes)) != ORX_OK) return rc;
+    if ((rc = ensure(&a.d_agg, &a.cap_agg, sizeof(OrxLeafResult) * (size_t)n_leaves)) != ORX_OK) return rc;
+    if (want_games && (rc = ensure(&a.d_games, &a.cap_games, sizeof(OrxGameResult) * total)) != ORX_OK) return rc;
+    CK(cudaMemcpyAsync(a.d_leaves, leaves, lbytes, cudaMemcpyHostToDevice, a.stream));
+    CK(cudaMemsetAsync(a.d_agg, 0, sizeof(OrxLeafResult) * (size_t)n_leaves, a.stream));
+    RolloutArgs ar;
+    memset(&ar, 0, sizeof ar);
+    ar.leaves = (const uint8_t *)a.d_leaves; ar.n_leaves = n_leaves; ar.playouts_per_leaf = playouts_per_leaf; ar.total = total;
+    ar.seed = seed; ar.first_game = first_game; ar.agg = (OrxLeafResult *)a.d_agg;
+    ar.games = want_games ? (OrxGameResult *)a.d_games : nullptr; ar.ticket = a.d_ticket;
+    if ((rc = launch_rollout(c, false, ar, a.stream)) != ORX_OK) return rc;
+    a.n_leaves = n_leaves; a.ppl = playouts_per_leaf; a.want_games = want_games != 0; a.busy = true;
+    return ORX_OK;
+}
+
+extern "C" int orx_rollout_end(OrxCtx *c, int slot, OrxLeafResult *agg, OrxGameResult *games)
+{
+    if (!c || slot < 0 || slot > 1) return set_err(ORX_E_INVALID, "bad argument");
+    OrxCtx::AsyncSlot &a = c->aslot[slot];
+    if (!a.busy) return set_err(ORX_E_INVALID, "slot is not in flight");
+    CK(cudaSetDevice(c->device));
+    if (agg) CK(cudaMemcpyAsync(agg, a.d_agg, sizeof(OrxLeafResult) * (size_t)a.n_leaves, cudaMemcpyDeviceToHost, a.stream));
+    if (games && a.want_games)
+        CK(cudaMemcpyAsync(games, a.d_games, sizeof(OrxGameResult) * (size_t)a.n_leaves * (size_t)a.ppl, cudaMemcpyDeviceToHost, a.stream));
+    cudaError_t e = cudaStreamSynchronize(a.stream);
+    a.busy = false;
+    if (e != cudaSuccess) return set_err(ORX_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
     return ORX_OK;
 }
 

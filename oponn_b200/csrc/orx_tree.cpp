@@ -819,17 +819,63 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
     for (int i = 0; i < (int)rootMoves.size(); i++) nodes[0].unvisitedRootIndex.push_back(i);
 
     struct Pending { std::vector<int> path; bool terminal; int pot[MAXP]; int finalTurn; };
-    std::vector<uint8_t> leaves;
-    std::vector<Pending> pend;
+    // Two batches in flight (orx_rollout_begin / _end on two streams): while the GPU plays one, the host selects the
+    // next under the virtual loss of both; a batch's tail (it ends with its longest game) overlaps the next one.
+    struct Batch { std::vector<uint8_t> leaves; std::vector<Pending> pend; int nleaf = 0; bool outstanding = false; clk::time_point t_begin; };
+    Batch batch[2];
     std::vector<OrxGameResult> games;
-    std::vector<OrxLeafResult> agg;
+    const int slots = O.leaves_in_flight >= 2 ? 2 : 1;
+    const int per_batch = std::max(1, O.leaves_in_flight / slots);
 
-    int done = 0;
-    while (done < iterations && !(nodes[0].children.size() == 1 && nodes[0].unvisited.empty())) {
+    auto finish = [&](int sl) -> int {
+        Batch &B = batch[sl];
+        auto t1 = clk::now();
+        if (B.nleaf) {
+            games.resize((size_t)B.nleaf * ppl);
+            int rc = orx_rollout_end(t->ctx, sl, nullptr, games.data());
+            if (rc != ORX_OK) return rc;
+        }
+        auto t2 = clk::now();
+        // --- back-propagation (:399-431)
+        int li = 0;
+        for (Pending &pd : B.pend) {
+            for (int j = 0; j < ppl; j++) {
+                const int *pot; int finalTurn;
+                if (pd.terminal) { pot = pd.pot; finalTurn = pd.finalTurn; }
+                else {
+                    const OrxGameResult &g = games[(size_t)li * ppl + j];
+                    if (g.flags & ORX_FLAG_ERROR) continue;  // an illegal leaf: nothing to learn from it
+                    pot = g.player_out_on_turn; finalTurn = g.sim_turn_count;
+                }
+                for (int n : pd.path) {
+                    Node &nd = nodes[n];
+                    for (int p = 0; p < P; p++) {
+                        if (pot[p] == -1) { nd.wins[p]++; nd.winLen[p] += finalTurn; } else { nd.losses[p]++; nd.lossLen[p] += finalTurn; }
+                    }
+                    nd.visits++;
+                }
+            }
+            for (int n : pd.path) nodes[n].inflight--;
+            if (!pd.terminal) li++;
+        }
+        B.outstanding = false;
+        auto t3 = clk::now();
+        st.rollout_ms += ms(t1, t2); st.backprop_ms += ms(t2, t3);
+        return ORX_OK;
+    };
+
+    int done = 0, scheduled = 0, sl = 0;
+    for (;;) {
+        if (batch[sl].outstanding) { int rc = finish(sl); if (rc != ORX_OK) return rc; done += (int)batch[sl].pend.size(); }
+        const bool forced = nodes[0].children.size() == 1 && nodes[0].unvisited.empty();   // (:179)
+        if (scheduled < iterations && !forced) {
         auto t0 = clk::now();
-        int want = std::min(O.leaves_in_flight, iterations - done);
-        leaves.clear(); pend.clear();
+        Batch &B = batch[sl];
+        int want = std::min(per_batch, iterations - scheduled);
+        B.leaves.clear(); B.pend.clear();
         int nleaf = 0;
+        std::vector<uint8_t> &leaves = B.leaves;
+        std::vector<Pending> &pend = B.pend;
         for (int b = 0; b < want; b++) {
             // --- selection (:186-198) under virtual loss
             board.setup((const uint8_t *)root_leaf, (const uint8_t *)extra);
@@ -879,9 +925,6 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
                 cur = pick;
             }
             if (board.error) return ORX_E_INVALID;
-            if (ongoing && nodes[cur].unvisited.empty()) {
-                // a node whose every move is in flight or that has no move at all: evaluate it as it stands
-            }
             if (ongoing && !nodes[cur].unvisited.empty()) {
                 // --- expansion (:335-355)
                 int k = rng.below((int)nodes[cur].unvisited.size());
@@ -915,40 +958,21 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
             pend.push_back(std::move(pd));
         }
         auto t1 = clk::now();
-        // --- simulation (:359-395): every leaf of the batch x playouts_per_leaf playouts, one call
+        st.select_ms += ms(t0, t1);
+        // --- simulation (:359-395): every leaf of the batch x playouts_per_leaf playouts, one launch
+        B.nleaf = nleaf;
         if (nleaf) {
-            games.resize((size_t)nleaf * ppl); agg.resize(nleaf);
-            int rc = orx_rollout_batch(t->ctx, leaves.data(), nleaf, ppl, O.seed, t->games, agg.data(), games.data());
+            int rc = orx_rollout_begin(t->ctx, sl, leaves.data(), nleaf, ppl, O.seed, t->games, 1);
             if (rc != ORX_OK) return rc;
             t->games += (unsigned long long)nleaf * ppl;
             st.batches++;
         }
-        auto t2 = clk::now();
-        // --- back-propagation (:399-431)
-        int li = 0;
-        for (Pending &pd : pend) {
-            for (int j = 0; j < ppl; j++) {
-                const int *pot; int finalTurn;
-                if (pd.terminal) { pot = pd.pot; finalTurn = pd.finalTurn; }
-                else {
-                    const OrxGameResult &g = games[(size_t)li * ppl + j];
-                    if (g.flags & ORX_FLAG_ERROR) continue;  // an illegal leaf: nothing to learn from it
-                    pot = g.player_out_on_turn; finalTurn = g.sim_turn_count;
-                }
-                for (int n : pd.path) {
-                    Node &nd = nodes[n];
-                    for (int p = 0; p < P; p++) {
-                        if (pot[p] == -1) { nd.wins[p]++; nd.winLen[p] += finalTurn; } else { nd.losses[p]++; nd.lossLen[p] += finalTurn; }
-                    }
-                    nd.visits++;
-                }
-            }
-            for (int n : pd.path) nodes[n].inflight--;
-            if (!pd.terminal) li++;
+        B.outstanding = true;
+        scheduled += (int)pend.size();
+        } else if (!batch[sl ^ 1].outstanding) {
+            break;
         }
-        done += (int)pend.size();
-        auto t3 = clk::now();
-        st.select_ms += ms(t0, t1); st.rollout_ms += ms(t1, t2); st.backprop_ms += ms(t2, t3);
+        if (slots == 2) sl ^= 1;
     }
     st.iterations = done; st.playouts = (int64_t)done * ppl; st.nodes = (int64_t)nodes.size();
     if (stats) *stats = st;

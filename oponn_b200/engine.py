@@ -57,6 +57,8 @@ def load_library():
     L.orx_rollout_batch.argtypes = [vp, vp, C.c_int, C.c_int, u64, u64, vp, vp]; L.orx_rollout_batch.restype = C.c_int
     L.orx_rollout_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, u64, u64, vp, vp]
     L.orx_rollout_batch_device.restype = C.c_int
+    L.orx_rollout_begin.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, u64, u64, C.c_int]; L.orx_rollout_begin.restype = C.c_int
+    L.orx_rollout_end.argtypes = [vp, C.c_int, vp, vp]; L.orx_rollout_end.restype = C.c_int
     L.orx_rollout_replay.argtypes = [vp, vp, C.c_int, vp, u32, vp]; L.orx_rollout_replay.restype = C.c_int
     L.orx_sync.argtypes = [vp]; L.orx_sync.restype = C.c_int
     L.orx_stream.argtypes = [vp]; L.orx_stream.restype = vp
@@ -77,7 +79,7 @@ def load_library():
 
 #: every symbol include/orx.h declares (checked by tests/test_abi.py)
 EXPORTS = ("orx_create", "orx_destroy", "orx_last_error", "orx_leaf_stride", "orx_rollout_batch",
-           "orx_rollout_batch_device", "orx_rollout_replay", "orx_sync", "orx_stream", "orx_last_kernel_ms",
+           "orx_rollout_batch_device", "orx_rollout_begin", "orx_rollout_end", "orx_rollout_replay", "orx_sync", "orx_stream", "orx_last_kernel_ms",
            "orx_kernel_launches", "orx_get_attack_outcomes", "orx_simulate_battles", "orx_simulate_individual",
            "orx_stream_draws", "orx_card_cash_value")
 
@@ -146,6 +148,20 @@ class RolloutEngine:
         """DEVICE pointers (e.g. ``torch.Tensor.data_ptr()``), asynchronous on the engine's stream."""
         self._ck(self._L.orx_rollout_batch_device(self._h, leaves_ptr, n_leaves, playouts_per_leaf, seed, first_game,
                                                   agg_ptr, games_ptr))
+
+    def rollout_begin(self, slot: int, leaves, playouts_per_leaf: int, seed: int, first_game: int = 0, per_game: bool = False):
+        """launch on one of the two in-flight slots; pair with :meth:`rollout_end`"""
+        lv = self._leaves(leaves)
+        self._ck(self._L.orx_rollout_begin(self._h, slot, lv.ctypes.data, lv.shape[0], playouts_per_leaf, seed, first_game,
+                                           int(per_game)))
+        return lv.shape[0], playouts_per_leaf, per_game
+
+    def rollout_end(self, slot: int, ticket):
+        n, ppl, per_game = ticket
+        agg = np.zeros(n, dtype=LEAF_RESULT_DTYPE)
+        games = np.zeros(n * ppl, dtype=GAME_RESULT_DTYPE) if per_game else None
+        self._ck(self._L.orx_rollout_end(self._h, slot, agg.ctypes.data, games.ctypes.data if per_game else None))
+        return agg, games
 
     def rollout_replay(self, leaves, words: np.ndarray) -> np.ndarray:
         """Game g plays leaf g on the injected word stream ``words[g]`` (replayed dice/move stream)."""

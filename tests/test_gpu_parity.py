@@ -296,3 +296,21 @@ def test_reference_facing_board_api(engine, classic, mid_leaf):
         bs.simulateIndividualBattle(4, 2)
     rows = bs.getAttackOutcomes(3, 2)
     assert abs(sum(r["probability"] for r in rows) - 1.0) < 1e-3
+
+
+def test_two_slots_in_flight_equal_the_blocking_call(engine, mid_leaf):
+    """orx_rollout_begin / _end on both slots at once == two orx_rollout_batch calls"""
+    leaves = np.fromfile(os.path.join(GOLDEN, "classic42_mid_64.leaves"), dtype=np.uint8).reshape(64, -1)
+    t0 = engine.rollout_begin(0, leaves[:40], 6, 9, first_game=1000, per_game=True)
+    t1 = engine.rollout_begin(1, mid_leaf[None, :], 300, 9, first_game=5000, per_game=True)
+    a1, g1 = engine.rollout_end(1, t1)
+    a0, g0 = engine.rollout_end(0, t0)
+    b0, h0 = engine.rollout_batch(leaves[:40], 6, 9, first_game=1000, per_game=True)
+    b1, h1 = engine.rollout_batch(mid_leaf[None, :], 300, 9, first_game=5000, per_game=True)
+    assert a0.tobytes() == b0.tobytes() and g0.tobytes() == h0.tobytes()
+    assert a1.tobytes() == b1.tobytes() and g1.tobytes() == h1.tobytes()
+    from oponn_b200.engine import OrxError
+    t0 = engine.rollout_begin(0, mid_leaf[None, :], 2, 1)
+    with pytest.raises(OrxError):
+        engine.rollout_begin(0, mid_leaf[None, :], 2, 1)        # slot still in flight
+    engine.rollout_end(0, t0)
