@@ -314,3 +314,13 @@ def test_two_slots_in_flight_equal_the_blocking_call(engine, mid_leaf):
     with pytest.raises(OrxError):
         engine.rollout_begin(0, mid_leaf[None, :], 2, 1)        # slot still in flight
     engine.rollout_end(0, t0)
+
+
+def test_65536_games_vs_oracle(engine, oracle, mid_leaf):
+    """BASELINE config 2: every per-game record of the first 65,536 games of the bench batch equals the oracle's
+    (about 30 s of oracle time on 16 host threads)"""
+    n = 1 << 16
+    agg, games = engine.rollout_batch(mid_leaf[None, :], n, RUN_SEED, per_game=True)
+    oagg, ogames = oracle.rollout_batch(mid_leaf[None, :], n, RUN_SEED, per_game=True, threads=THREADS)
+    same(games, ogames)
+    assert agg.tobytes() == oagg.tobytes()
