@@ -86,6 +86,11 @@ int orx_tree_possible_moves(OrxTree *t, const void *leaf, const void *extra, Orx
 int orx_tree_apply(OrxTree *t, const void *leaf, const void *extra, const OrxMove *move, void *leaf_out,
                    void *extra_out, int32_t *ongoing);
 
+/* Replaces SimulationBoard.setupNewGame (SimulationBoard.java:141-176): the territories are shuffled
+ * (Collections.shuffle with java.util.Random(seed)) and dealt round-robin with one army each; the record starts
+ * player 0's INITIAL_PLACEMENT with setupInitialPlacementPhase's allowance; nobody holds cards. */
+int orx_new_game(const OrxMap *map, uint64_t seed, void *leaf_out);
+
 /* One root child after a search, in getPossibleMoves() order of the root (so that independent trees merge by
  * index: root-parallel mode, one all-reduce of these integers per move). */
 typedef struct OrxRootChild {

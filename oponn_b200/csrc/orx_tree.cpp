@@ -761,6 +761,33 @@ extern "C" int orx_tree_apply(OrxTree *t, const void *leaf, const void *extra, c
     return ORX_OK;
 }
 
+extern "C" int orx_new_game(const OrxMap *map, uint64_t seed, void *leaf_out)
+{
+    if (!map || !leaf_out) return ORX_E_INVALID;
+    const int N = map->n_territories, P = map->n_players;
+    if (N < 1 || N > ORX_MAX_TERRITORIES || P < 2 || P > MAXP) return ORX_E_INVALID;
+    OrxLeafLayout L = orx_leaf_layout(N, P);
+    uint8_t *leaf = (uint8_t *)leaf_out;
+    memset(leaf, 0, (size_t)L.stride);
+    std::vector<int> ccs(N);
+    for (int i = 0; i < N; i++) ccs[i] = i;
+    JavaRandom rnd; rnd.set_seed(seed);
+    for (int i = N; i > 1; i--) std::swap(ccs[i - 1], ccs[rnd.next_int(i)]);   // Collections.shuffle(list, rnd)
+    uint8_t *ow = leaf + L.off_owner; int32_t *ar = (int32_t *)(leaf + L.off_armies); uint8_t *cards = leaf + L.off_cards;
+    int player = 0, owned0 = 0;
+    for (int cc : ccs) { ow[cc] = (uint8_t)player; ar[cc] = 1; owned0 += player == 0; player = (player + 1) % P; }
+    double f1 = N / 42.0; f1 -= 1.0; f1 /= 2.0; f1 += 1.0;
+    int left0 = (int)floor(f1 * (50 - P * 5) + 0.5) - owned0;             // calculateStartingArmies()[0] - playerCountries[0]
+    OrxLeafHeader *h = (OrxLeafHeader *)leaf;
+    h->turn_count = 0; h->placeable = left0 == 5 ? 5 : (left0 < 4 ? left0 : 4);
+    h->attacking_cc = -1; h->defending_cc = -1; h->card_pos = 0; h->current_player = 0; h->phase = ORX_PHASE_INITIAL_PLACEMENT;
+    h->attack_state = ORX_ATTACK_START; h->defending_player = -1; h->attack_until_dead = 1;
+    h->n_hand = 0; h->n_deck = (uint8_t)(N + 2);
+    for (int i = 0; i < N; i++) cards[i] = (uint8_t)i;                      // CardManager's notInHand: every card, then two wildcards
+    cards[N] = ORX_CARD_WILD; cards[N + 1] = ORX_CARD_WILD;
+    return ORX_OK;
+}
+
 extern "C" int orx_tree_choose(const OrxTree *t, const OrxRootChild *ch, int n, uint64_t tie_break)
 {
     if (!t || !ch || n <= 0) return ORX_E_INVALID;

@@ -73,12 +73,24 @@ def _bind(L):
     L.orx_tree_apply.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32)]; L.orx_tree_apply.restype = C.c_int
     L.orx_tree_search.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int32), vp]; L.orx_tree_search.restype = C.c_int
     L.orx_tree_choose.argtypes = [vp, vp, C.c_int, C.c_uint64]; L.orx_tree_choose.restype = C.c_int
+    L.orx_new_game.argtypes = [C.POINTER(OrxMapC), C.c_uint64, vp]; L.orx_new_game.restype = C.c_int
     L._tree_bound = True
     return L
 
 
-TREE_EXPORTS = ("orx_tree_default_options", "orx_tree_create", "orx_tree_destroy", "orx_tree_possible_moves",
+TREE_EXPORTS = ("orx_new_game", "orx_tree_default_options", "orx_tree_create", "orx_tree_destroy", "orx_tree_possible_moves",
                 "orx_tree_apply", "orx_tree_search", "orx_tree_choose")
+
+
+def new_game(risk_map: RiskMap, seed: int) -> np.ndarray:
+    """SimulationBoard.setupNewGame (SimulationBoard.java:141-176) as a packed leaf record."""
+    L = _bind(load_library())
+    mc = risk_map.to_c()
+    out = np.zeros(leaf_layout(risk_map.n_territories, risk_map.n_players).stride, dtype=np.uint8)
+    rc = L.orx_new_game(C.byref(mc), seed, out.ctypes.data)
+    if rc != ORX_OK:
+        raise OrxError(rc, "orx_new_game rejected the map")
+    return out
 
 
 def move_str(m) -> str:

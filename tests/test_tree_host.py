@@ -207,3 +207,27 @@ def test_random_walk_produces_legal_leaves(classic, mid_leaf, oracle):
     _, games = oracle.rollout_batch(np.stack(visited), 1, 77, per_game=True, threads=8)
     assert np.all(games["flags"] == 0)
     assert np.all((games["player_out_on_turn"][:, :6] == -1).sum(axis=1) == 1)
+
+
+def test_new_game_setup(classic, oracle):
+    """setupNewGame (SimulationBoard.java:141-176): a shuffled round-robin deal, one army each, player 0 about to place"""
+    from javarandom import JavaRandom
+    from oponn_b200.tree import new_game
+    leaf = new_game(classic, 12345)
+    s = BoardState.unpack(classic, leaf)
+    # Collections.shuffle(list, rnd): for i = size .. 2 swap(i - 1, rnd.nextInt(i))
+    r = JavaRandom(12345); ccs = list(range(42))
+    for i in range(42, 1, -1):
+        j = r.nextInt(i); ccs[i - 1], ccs[j] = ccs[j], ccs[i - 1]
+    want = [0] * 42
+    for k, cc in enumerate(ccs):
+        want[cc] = k % 6
+    assert s.owner == want and s.armies == [1] * 42
+    assert (s.currentPlayer, s.currentPhase, s.turnCount, s.numberOfPlaceableArmies) == (0, PHASE_INITIAL_PLACEMENT, 0, 4)
+    assert len(s.hand) == 0 and len(s.deck) == 44 and s.deck.count(CARD_WILD) == 2
+    # the record is a legal rollout start and a legal tree root
+    _, games = oracle.rollout_batch(leaf[None, :], 4, 3, per_game=True)
+    assert np.all(games["flags"] == 0) and np.all((games["player_out_on_turn"][:, :6] == -1).sum(axis=1) == 1)
+    t = SearchTree(classic, Rules())
+    assert all(int(m["type"]) == MOVE_INITIAL_PLACEMENT for m in t.getPossibleMoves(leaf))
+    t.close()
