@@ -364,7 +364,7 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
             const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
             int l = lane_id();
             saddr p0 = s.buf + 4u * s.wi + 8u * (uint32_t)l;
-            int lo = ra < rd ? ra : rd, hi = ra < rd ? rd : ra;
+            int hi = ra < rd ? rd : ra;
             int slack = 2 * (avail - 1);  // armies lost before the last roll of the step, at most
             if (avail >= 32 && ra - slack >= 3 && rd - slack >= 2 && hi - slack > 100) {
                 int x = 0;
@@ -381,7 +381,6 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
                 s.wi += 2u * (uint32_t)avail;
                 continue;
             }
-            (void)lo;
             if (avail > 32) avail = 32;
             int x = 0;
             if (l < avail) {

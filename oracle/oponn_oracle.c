@@ -397,6 +397,7 @@ int orc_get_attack_outcomes(int a, int d, float *prob, int32_t *al, int32_t *dl,
 
 typedef struct Counters { /* algorithmic work, SURVEY.md 8(d) */
     uint64_t tv, ev, r_words, battles, cdf_steps, writes, player_turns, attacks, conquests, single_rolls, gauss_battles, table_battles;
+    uint64_t cls[8]; /* battle classes by size: see simulateBattle */
 } Counters;
 
 static int ceil_log2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
@@ -414,6 +415,11 @@ static int simulateIndividualBattle(Stream *s, int attackers, int defenders)
 static void simulateBattle(Stream *s, Counters *ct, int attackers, int defenders, int *alOut, int *dlOut)
 {
     int attackerLosses = 0, defenderLosses = 0;
+    if (ct) { /* workload statistics only */
+        int c = attackers > 100 ? (defenders == 1 ? 0 : defenders == 2 ? 1 : defenders <= 100 ? 2 : 3)
+                                : (defenders > 100 ? (attackers == 1 ? 4 : attackers == 2 ? 5 : 6) : 7);
+        ct->cls[c]++;
+    }
     if (attackers > 500 && defenders > 500) {
         int matchedAttackers = java_d2i(0.922 * defenders);
         if (ct) ct->gauss_battles++;
@@ -1341,6 +1347,7 @@ static void run_one(Board *b, const OrcCtx *c, const uint8_t *leaf, uint64_t see
         ct_acc->cdf_steps += b->ct.cdf_steps; ct_acc->writes += b->ct.writes; ct_acc->player_turns += b->ct.player_turns;
         ct_acc->attacks += b->ct.attacks; ct_acc->conquests += b->ct.conquests;
         ct_acc->single_rolls += b->ct.single_rolls; ct_acc->gauss_battles += b->ct.gauss_battles; ct_acc->table_battles += b->ct.table_battles;
+        for (int k = 0; k < 8; k++) ct_acc->cls[k] += b->ct.cls[k];
     }
 }
 
@@ -1381,7 +1388,7 @@ static void *batch_worker(void *arg)
 
 /* setupState + simulate + getters for n_leaves x playouts_per_leaf playouts.
  * Game ids are first_game + leaf*playouts_per_leaf + k, so any sharding gives the same
- * per-game results.  agg (n_leaves) and counters (12 x u64) may be NULL; games may be NULL. */
+ * per-game results.  agg (n_leaves) and counters (20 x u64) may be NULL; games may be NULL. */
 int orc_rollout_batch(const OrcCtx *ctx, const uint8_t *leaves, int n_leaves, int playouts_per_leaf,
                       uint64_t seed, uint64_t first_game, OrxLeafResult *agg, OrxGameResult *games,
                       uint64_t *counters, int nthreads)
@@ -1409,12 +1416,13 @@ int orc_rollout_batch(const OrcCtx *ctx, const uint8_t *leaves, int n_leaves, in
             }
     }
     if (counters) {
-        memset(counters, 0, 12 * sizeof(uint64_t));
+        memset(counters, 0, 20 * sizeof(uint64_t));
         for (int t = 0; t < nthreads; t++) {
             const Counters *c = &jobs[t].ct;
             counters[0] += c->tv; counters[1] += c->ev; counters[2] += c->r_words; counters[3] += c->battles; counters[4] += c->cdf_steps;
             counters[5] += c->writes; counters[6] += c->player_turns; counters[7] += c->attacks; counters[8] += c->conquests;
             counters[9] += c->single_rolls; counters[10] += c->gauss_battles; counters[11] += c->table_battles;
+            for (int k = 0; k < 8; k++) counters[12 + k] += c->cls[k];
         }
     }
     free(aggs); free(th); free(jobs);

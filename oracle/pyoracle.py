@@ -120,7 +120,8 @@ def starting_armies(n_territories: int, n_players: int):
 
 
 COUNTER_NAMES = ("tv", "ev", "r_words", "battles", "cdf_steps", "writes", "player_turns", "attacks", "conquests",
-                 "single_rolls", "gauss_battles", "table_battles")
+                 "single_rolls", "gauss_battles", "table_battles",
+                 "b_big_v_1", "b_big_v_2", "b_big_v_3to100", "b_big_v_big", "b_1_v_big", "b_2_v_big", "b_3to100_v_big", "b_small_v_small")
 
 
 class Oracle:
@@ -149,7 +150,7 @@ class Oracle:
         n = leaves.shape[0]
         agg = np.zeros(n, dtype=self._ldt)
         games = np.zeros(n * playouts_per_leaf, dtype=self._gdt) if per_game else None
-        ct = np.zeros(12, dtype=np.uint64)
+        ct = np.zeros(20, dtype=np.uint64)
         rc = lib().orc_rollout_batch(self._h, _p(leaves, C.c_uint8), n, playouts_per_leaf, seed, first_game,
                                      agg.ctypes.data, games.ctypes.data if per_game else None,
                                      _p(ct, C.c_uint64), threads)
