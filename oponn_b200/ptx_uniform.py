@@ -6,8 +6,9 @@ wraps every such branch in BSSY/BSYNC and guards every ``*.sync`` instruction wi
 executed instructions in profile r1b were convergence bookkeeping.  ``bra.uni`` is PTX's way to promise that all
 active threads of the warp take the branch together; this pass derives that promise conservatively.
 
-Analysis (per function, flow-insensitive, to a fixed point):
-  * lane-variant seeds: %laneid, %tid, %lanemask_*, atomics, call results, values loaded from call return slots;
+Analysis (per function; a forward data-flow over the CFG, iterated with control dependence to a fixed point):
+  * lane-variant seeds: %laneid, %tid, %lanemask_*, atomics, call results, values loaded from call return slots,
+    loads from local (thread-private) or generic address space;
   * a destination is variant if any source register, its guard predicate or (for loads) its address is variant;
   * warp-collectives make uniform values whatever their inputs: vote.sync, redux.sync, and shfl.sync.idx whose
     source-lane / clamp / mask operands are uniform;
@@ -263,9 +264,11 @@ def analyse(lines: List[str], lo: int, hi: int) -> Tuple[List[int], int]:
     pre = []   # per instruction: (kind, dest mask, source mask, guard mask, is conditional branch)
     for i in ins:
         op, t = i.op, i.text
-        if any(s_ in t for s_ in VARIANT_SREGS) or op.startswith("atom.") or op.startswith("activemask") or \
+        generic_or_local_load = op.startswith("ld.") and not any(
+            op.startswith(p_) for p_ in ("ld.global", "ld.shared", "ld.param", "ld.const", "ld.volatile.shared", "ld.volatile.global"))
+        if any(s_ in t for s_ in VARIANT_SREGS) or op.startswith("atom.") or op.startswith("activemask") or generic_or_local_load or \
                 (op.startswith("ld.param") and "retval" in t) or (op.startswith("shfl.sync") and not op.startswith("shfl.sync.idx")):
-            kind, src = KIND_SEED, 0
+            kind, src = KIND_SEED, 0   # thread-private (local) and generic loads may differ per lane even at one address
         elif op.startswith("vote.sync") or op.startswith("redux.sync"):
             kind, src = KIND_UNI, 0
         elif op.startswith("shfl.sync.idx"):

@@ -132,3 +132,55 @@ def invalid_leaves(m, base: np.ndarray) -> np.ndarray:
         b[L.off_ncards:L.off_ncards + p] = 40
     mutate(too_many_hidden_cards)
     return np.stack(out)
+
+
+def random_map(rng, n_territories: int, n_players: int, n_continents: int):
+    """a connected random graph with bounded degree, random continents (possibly empty ones) and bonuses"""
+    from oponn_b200.state import RiskMap
+    n = n_territories
+    nb = [set() for _ in range(n)]
+    order = rng.permutation(n)
+    for i in range(1, n):                       # random spanning tree
+        a = int(order[i]); b = int(order[rng.integers(i)])
+        if len(nb[a]) < 12 and len(nb[b]) < 12:
+            nb[a].add(b); nb[b].add(a)
+        else:
+            c = next(int(x) for x in order[:i] if len(nb[int(x)]) < 12)
+            nb[a].add(c); nb[c].add(a)
+    for _ in range(int(n * rng.uniform(0.3, 1.5))):  # extra borders
+        a, b = int(rng.integers(n)), int(rng.integers(n))
+        if a != b and len(nb[a]) < 12 and len(nb[b]) < 12:
+            nb[a].add(b); nb[b].add(a)
+    adjacency = []
+    for t in range(n):
+        lst = sorted(nb[t]); rng.shuffle(lst); adjacency.append([int(x) for x in lst])
+    cont = [int(x) for x in rng.integers(n_continents, size=n)]
+    bonus = [int(x) for x in rng.integers(0, 8, size=n_continents)]
+    sym = [int(x) for x in rng.integers(3, size=n)] if rng.random() < 0.5 else None
+    return RiskMap(name=f"rand{n}", n_players=n_players, adjacency=adjacency, continent=cont, continent_bonus=bonus, card_symbol=sym)
+
+
+def random_leaves(m, rng, count: int) -> np.ndarray:
+    """random legal mid-game records in the four turn phases (every player may or may not be alive)"""
+    n, p = m.n_territories, m.n_players
+    out = []
+    for _ in range(count):
+        alive = [int(x) for x in rng.permutation(p)[:int(rng.integers(2, p + 1))]]
+        owner = [alive[int(rng.integers(len(alive)))] for _ in range(n)]
+        cp = owner[int(rng.integers(n))]
+        scale = int(rng.choice([3, 10, 60, 400, 2000]))
+        armies = [int(x) for x in rng.integers(1, scale + 1, size=n)]
+        cards = list(range(n)) + [CARD_WILD, CARD_WILD]
+        rng.shuffle(cards)
+        nh = int(rng.integers(0, 7))
+        hand, rest = [int(c) for c in cards[:nh]], [int(c) for c in cards[nh:]]
+        ncards = [int(rng.integers(0, 5)) if q in alive and q != cp else 0 for q in range(p)]
+        while sum(ncards) > len(rest):
+            ncards[int(np.argmax(ncards))] -= 1
+        phase = int(rng.choice([PHASE_CARDS, PHASE_PLACEMENT, PHASE_ATTACK, PHASE_FORTIFICATION]))
+        b = BoardState(owner=owner, armies=armies, currentPlayer=cp, currentPhase=phase, turnCount=int(rng.integers(0, 30)),
+                       playerNumberOfCards=ncards, numberOfPlaceableArmies=int(rng.integers(0, 40)) if phase != PHASE_ATTACK else 0,
+                       hasInvadedACountry=bool(rng.integers(2)), attackState=ATTACK_START, cardProgressionPos=int(rng.integers(0, 30)),
+                       hand=hand, deck=rest)
+        out.append(b.pack(m))
+    return np.stack(out)

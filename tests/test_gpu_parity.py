@@ -324,3 +324,25 @@ def test_65536_games_vs_oracle(engine, oracle, mid_leaf):
     oagg, ogames = oracle.rollout_batch(mid_leaf[None, :], n, RUN_SEED, per_game=True, threads=THREADS)
     same(games, ogames)
     assert agg.tobytes() == oagg.tobytes()
+
+
+def test_random_maps_and_leaves_fuzz():
+    """random graphs (both kernel widths), 2..8 players, random rules and random legal records: every game record equal"""
+    from leafzoo import random_leaves, random_map
+    rng = np.random.default_rng(20261020)
+    progs = ["4, 6, 8, 10, 15, 20...", "5, 5, 5...", "4, 5, 6...", "3, 6, 9...", "4, 6, 8, 10, 15, 20, 25, 10, 10, 10..."]
+    for k in range(12):
+        n = int(rng.choice([5, 12, 31, 32, 33, 42, 64, 65, 90, 150]))
+        p = int(rng.integers(2, 9))
+        m = random_map(rng, n, p, int(rng.integers(1, 9)))
+        r = Rules(use_cards=bool(rng.random() < 0.8), transfer_cards=bool(rng.integers(2)), continent_increase=int(rng.choice([0, 0, 3, 10])),
+                  card_progression=str(rng.choice(progs)), max_player_turns=int(rng.choice([300, 2000])))
+        leaves = random_leaves(m, rng, 160 if n <= 64 else 60)
+        e, o = pair(m, r)
+        try:
+            agg, games = e.rollout_batch(leaves, 2, 1234 + k, per_game=True)
+            oagg, ogames = o.rollout_batch(leaves, 2, 1234 + k, per_game=True, threads=THREADS)
+            same(games, ogames)
+            assert agg.tobytes() == oagg.tobytes()
+        finally:
+            e.close(); o.close()
