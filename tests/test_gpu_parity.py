@@ -346,3 +346,18 @@ def test_random_maps_and_leaves_fuzz():
             assert agg.tobytes() == oagg.tobytes()
         finally:
             e.close(); o.close()
+
+
+def test_win_rates_under_normal_seeding(engine, oracle, mid_leaf):
+    """North-star correctness part 2: with ordinary (different) seeds the engine's root win-rate estimates agree with
+    the CPU simulator's within a stated confidence interval: per player, |p_gpu - p_cpu| < 4.5 sigma of the difference
+    of two binomial estimates (a 1-in-10^5 event per player if the two samplers are the same distribution)."""
+    n_gpu, n_cpu = 1 << 17, 1 << 13
+    agg, _ = engine.rollout_batch(mid_leaf[None, :], n_gpu, 555)
+    oagg, _ = oracle.rollout_batch(mid_leaf[None, :], n_cpu, 99991, per_game=False, threads=THREADS)
+    for p in range(6):
+        a, b = agg["wins"][0][p] / n_gpu, oagg["wins"][0][p] / n_cpu
+        sigma = np.sqrt(a * (1 - a) / n_gpu + b * (1 - b) / n_cpu)
+        assert abs(a - b) < 4.5 * sigma, (p, a, b, sigma)
+    la, lb = agg["len_sum"][0] / n_gpu, oagg["len_sum"][0] / n_cpu      # mean game length in rounds (std ~ 330)
+    assert abs(la - lb) < 4.5 * 330 * np.sqrt(1 / n_gpu + 1 / n_cpu), (la, lb)
