@@ -349,56 +349,55 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
         //   block   up to 64 rolls (2 per lane) when no roll of the step can end the loop or change the dice;
         //   scan    up to 32 rolls (1 per lane): the first roll after which the loop would stop is found by ballot.
         while ((ra > 100 || rd > 100) && ra > 0 && rd > 0 && !s.flags) {
-            int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
-            int avail = 0;
-            if (!REPLAY && ra > 2 && rd > 2) {
+            if (!REPLAY && ra > 2 && rd > 2) {   // 3 v 2 dice: lane-parallel steps over the doubles left in the block
                 if (s.wi == 128u) s.refill();
-                avail = (int)(128u - s.wi) >> 1;
-            }
-            if (avail == 0) {
-                int x = single_roll(dm, pa, pd, s.next_k53());
-                attackerLosses += x; defenderLosses += n - x; ra -= x; rd -= n - x;
-                continue;
-            }
-            // here pa == 3 and pd == 2: thresholds of row 5
-            const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
-            int l = lane_id();
-            saddr p0 = s.buf + 4u * s.wi + 8u * (uint32_t)l;
-            int hi = ra < rd ? rd : ra;
-            int slack = 2 * (avail - 1);  // armies lost before the last roll of the step, at most
-            if (avail >= 32 && ra - slack >= 3 && rd - slack >= 2 && hi - slack > 100) {
-                int x = 0;
-                {
-                    uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
-                    x = (k > t0) + (k > t1);
+                const int avail = (int)(128u - s.wi) >> 1;
+                if (avail > 0) {
+                    const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
+                    const int l = lane_id();
+                    const saddr p0 = s.buf + 4u * s.wi + 8u * (uint32_t)l;
+                    const int hi = ra < rd ? rd : ra;
+                    const int slack = 2 * (avail - 1);  // armies lost before the last roll of the step, at most
+                    if (avail >= 32 && ra - slack >= 3 && rd - slack >= 2 && hi - slack > 100) {
+                        int x = 0;
+                        {
+                            uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
+                            x = (k > t0) + (k > t1);
+                        }
+                        if (l + 32 < avail) {
+                            uint64_t k = ((uint64_t)(lds32(p0 + 256u) >> 6) << 27) + (uint64_t)(lds32(p0 + 260u) >> 5);
+                            x += (k > t0) + (k > t1);
+                        }
+                        int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 2 * avail - la;
+                        attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
+                        s.wi += 2u * (uint32_t)avail;
+                        continue;
+                    }
+                    const int np = avail > 32 ? 32 : avail;
+                    int x = 0;
+                    if (l < np) {
+                        uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
+                        x = (k > t0) + (k > t1);
+                    }
+                    // attacker losses up to and including roll l, from two ballots (x is 0, 1 or 2)
+                    uint32_t b1 = __ballot_sync(ORX_FULL, x >= 1), b2 = __ballot_sync(ORX_FULL, x == 2);
+                    uint32_t le = lanemask_le();
+                    int cumA = __popc(b1 & le) + __popc(b2 & le);
+                    int ra_l = ra - cumA, rd_l = rd - (2 * (l + 1) - cumA);
+                    bool go_on = (ra_l > 100 || rd_l > 100) && ra_l >= 3 && rd_l >= 2;
+                    uint32_t stop = __ballot_sync(ORX_FULL, !go_on || l >= np - 1);
+                    int last = __ffs(stop) - 1;  // rolls 0..last are played
+                    uint32_t upto = 0xFFFFFFFFu >> (31 - last);
+                    int la = __popc(b1 & upto) + __popc(b2 & upto), ld = 2 * (last + 1) - la;
+                    attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
+                    s.wi += 2u * (uint32_t)(last + 1);
+                    continue;
                 }
-                if (l + 32 < avail) {
-                    uint64_t k = ((uint64_t)(lds32(p0 + 256u) >> 6) << 27) + (uint64_t)(lds32(p0 + 260u) >> 5);
-                    x += (k > t0) + (k > t1);
-                }
-                int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 2 * avail - la;
-                attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
-                s.wi += 2u * (uint32_t)avail;
-                continue;
             }
-            if (avail > 32) avail = 32;
-            int x = 0;
-            if (l < avail) {
-                uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
-                x = (k > t0) + (k > t1);
-            }
-            // attacker losses up to and including roll l, from two ballots (x is 0, 1 or 2)
-            uint32_t b1 = __ballot_sync(ORX_FULL, x >= 1), b2 = __ballot_sync(ORX_FULL, x == 2);
-            uint32_t le = lanemask_le();
-            int cumA = __popc(b1 & le) + __popc(b2 & le);
-            int ra_l = ra - cumA, rd_l = rd - (2 * (l + 1) - cumA);
-            bool go_on = (ra_l > 100 || rd_l > 100) && ra_l >= 3 && rd_l >= 2;
-            uint32_t stop = __ballot_sync(ORX_FULL, !go_on || l >= avail - 1);
-            int last = __ffs(stop) - 1;  // rolls 0..last are played
-            uint32_t upto = 0xFFFFFFFFu >> (31 - last);
-            int la = __popc(b1 & upto) + __popc(b2 & upto), ld = 2 * (last + 1) - la;
-            attackerLosses += la; defenderLosses += ld; ra -= la; rd -= ld;
-            s.wi += 2u * (uint32_t)(last + 1);
+            // one roll: a side is down to its last armies, the next double straddles two blocks, or replay mode
+            const int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
+            const int x = single_roll(dm, pa, pd, s.next_k53());
+            attackerLosses += x; defenderLosses += n - x; ra -= x; rd -= n - x;
         }
         if (ra != 0 && rd != 0 && !s.flags) {
             if (ra < 0 || rd < 0 || ra > ORX_TABLE_LIMIT || rd > ORX_TABLE_LIMIT) {
