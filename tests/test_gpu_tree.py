@@ -88,3 +88,59 @@ def test_search_without_engine_refuses(classic, mid_leaf):
     with pytest.raises(OrxError):
         tree.search(mid_leaf, 10)
     tree.close()
+
+
+def test_native_search_vs_python_restatement(engine, oracle, classic, mid_leaf):
+    """orx_tree_search at leaves_in_flight = 1 against oracle/pymcts.py (MCTSTree.runMCTS restated in Python over
+    oracle/pyexplore.py, playouts by the CPU simulator).  Different random streams, so the comparison is statistical,
+    with the interval stated: the agent's root win rate within 4.5 sigma, and the same most-visited move family."""
+    import functools
+    import random
+
+    from oracle import pyexplore, pymcts, pyoracle
+
+    @functools.lru_cache(maxsize=None)
+    def outcomes(a, d):
+        pr, al, dl, inv = pyoracle.get_attack_outcomes(a, d)
+        return [(np.float32(p), int(x), int(y), bool(v)) for p, x, y, v in zip(pr, al, dl, inv)]
+
+    bs = attack_leaf(classic, mid_leaf)
+    iters, cores = 300, 8
+    tree = SearchTree(classic, Rules(), TreeOptions(agent_id=0, playouts_per_leaf=cores, leaves_in_flight=1, seed=21), engine)
+    ch, st = tree.search(bs, iters)
+
+    board = pyexplore.ExplorationBoard(classic, Rules(), outcomes)
+    game = [0]
+
+    class Rollout:
+        def __init__(self):
+            self.cores = cores
+
+        def __call__(self, b):
+            s = b.state()
+            leaf = BoardState(owner=s["owner"], armies=s["armies"], currentPlayer=s["currentPlayer"], currentPhase=s["currentPhase"],
+                              turnCount=s["turnCount"], playerNumberOfCards=s["playerNumberOfCards"],
+                              numberOfPlaceableArmies=s["numberOfPlaceableArmies"], hasInvadedACountry=s["hasInvadedACountry"],
+                              attackState=s["attackState"], attackingCC=s["attackingCC"], defendingCC=s["defendingCC"],
+                              defendingPlayer=s["defendingPlayer"], attackUntilDead=True, cardProgressionPos=b.real_pos,
+                              hand=b.real_hand, deck=b.real_deck).pack(classic)
+            _, games = oracle.rollout_batch(leaf[None, :], cores, 4711, first_game=game[0], per_game=True, threads=8)
+            game[0] += cores
+            return [([int(x) for x in g["player_out_on_turn"][:6]], int(g["sim_turn_count"])) for g in games]
+
+    rng = random.Random(5)
+    root, root_moves = pymcts.run_mcts(board, lambda: board.setup(bs), Rollout(), 0, 6, iters, rng)
+    tree.close()
+    # same root move list, in the same order
+    assert [(int(m["type"]), int(m["a"]), int(m["b"]), int(m["flag"])) for m in ch["move"]] == [(m[0], m[2], m[3], m[7]) for m in root_moves]
+    n1, n2 = int(ch["visits"].sum()), root.visits
+    assert n1 == n2 == iters * cores
+    p1, p2 = ch["wins"][:, 0].sum() / n1, root.wins[0] / n2
+    sigma = np.sqrt(p1 * (1 - p1) / n1 + p2 * (1 - p2) / n2)
+    assert abs(p1 - p2) < 4.5 * sigma + 0.02, (p1, p2, sigma)
+    # visit shares of the root children correlate (both searches prefer the same region of the move list)
+    v1 = ch["visits"] / n1
+    v2 = np.zeros(len(ch))
+    for c in root.children:
+        v2[root_moves.index(c.move)] = c.visits / n2
+    assert np.corrcoef(v1, v2)[0, 1] > 0.5, (v1, v2)
