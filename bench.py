@@ -51,6 +51,16 @@ def load_traffic(playouts: int):
     return d["traffic_bytes_per_launch"] if d.get("playouts_per_launch") == playouts else None
 
 
+def load_issue_active(playouts: int):
+    """smsp__issue_active.avg.pct_of_peak_sustained_active / 100 of the same launch size, from the committed ncu capture
+    (the layout-aware companion of roofline.frac: how full the issue slots actually are)."""
+    p = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["issue_active_pct"] / 100.0 if d.get("playouts_per_launch") == playouts else None
+
+
 def measured_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -271,6 +281,7 @@ def run_ours(args):
                                         f"({peaks['_source']} clock, MEASURED_PEAKS.json)",
                          "algorithmic_int_ops_per_playout": A, "kernel_ms_avg": k_avg_ms,
                          "traffic": load_traffic(P),
+                         "issue_slots_busy_ncu": load_issue_active(P),
                          "hbm_side_check": {"algorithmic_bytes_per_launch": alg_bytes,
                                             "achieved_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9,
                                             "peak_gbs": peaks["hbm_gbs"]}},
