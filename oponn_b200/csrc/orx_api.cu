@@ -420,6 +420,7 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
     {
         size_t tsm = 2 * sizeof(float) * (ORX_TABLE_LIMIT + 1) * (ORX_TABLE_LIMIT + 1);
         CKC(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        CKC(cudaMemsetAsync(c->d_rows, 0, sizeof(uint64_t) * kTableRows, c->stream));   // unused rows of a block stay zero
         build_tables_kernel<<<ORX_TABLE_LIMIT * ORX_TABLE_LIMIT, 256, tsm, c->stream>>>(c->d_meta, c->d_rows, c->d_probs);
         CKC(cudaGetLastError());
         c->launches++;

@@ -297,21 +297,25 @@ __device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
 // 32 rows are compared per step, one per lane.
 __device__ __forceinline__ void table_battle(const DevMap &dm, int a, int d, uint64_t k, int &al, int &dl)
 {
-    uint32_t meta = __ldg(dm.bt_meta + (a - 1) * ORX_TABLE_LIMIT + (d - 1));
-    const uint64_t *rows = dm.bt_rows + (meta >> 8);
-    int cnt = (int)(meta & 0xFFu);
-    uint64_t key = k << 11;
+    // Row block of (a, d): tables are laid out (a, d) row-major with capacity a + d each, unused rows zero (a zero
+    // threshold can only be reached by k = 0, which the first real row takes first), so neither the offset nor the
+    // row count needs the meta table: one dependent global load per battle instead of two.
+    const uint32_t off = (uint32_t)(50 * a * (a - 1) + 5050 * (a - 1) + a * (d - 1) + ((d * (d - 1)) >> 1));
+    const uint64_t *rows = dm.bt_rows + off;
+    const int cnt = a + d;
+    const uint64_t key = k << 11;
     al = 0; dl = 0;
     for (int base = 0; base < cnt; base += 32) {
         int i = base + lane_id();
         uint64_t t = i < cnt ? __ldg(rows + i) : 0ull;
-        uint32_t hit = __ballot_sync(ORX_FULL, i < cnt && key <= t);
+        uint32_t hit = __ballot_sync(ORX_FULL, key <= t);
         if (hit) {
             uint32_t code = __shfl_sync(ORX_FULL, (uint32_t)t & 0xFFu, __ffs(hit) - 1);
             int rem = (int)(code & 0x7Fu);
             if (code & 0x80u) { al = a - rem; dl = d; } else { al = a; dl = d - rem; }
             return;
         }
+        if (__ballot_sync(ORX_FULL, i < cnt && t == 0ull)) return;   // past the last real row: r above the total mass
     }
 }
 
