@@ -36,11 +36,19 @@ typedef struct OrxCtx OrxCtx;
  * (Oponn.java:106-110 -> SimulationBoard.java:102-139) and BattleSim's static table build
  * (BattleSim.java:46-59).  Copies map and rules, stages them on `device`, builds the battle
  * outcome tables for every (a, d) in 1..100 x 1..100 on the GPU.  All playout policies are
- * SimRandom (lux_agent_modelling=false). */
+ * SimRandom (lux_agent_modelling=false) until orx_set_sim_agents says otherwise. */
 int orx_create(const OrxMap *map, const OrxRules *rules, int device, OrxCtx **out);
 
 /* Replaces: letting the boards be garbage collected. */
 void orx_destroy(OrxCtx *ctx);
+
+/* Replaces: the `SimAgent[] sas` and `modellingTurnLimit` arguments of `new ModellingBoard(bs, sas, cm, cid, limit)`
+ * (ModellingBoard.java:13-19; built by Oponn.createSimAgents, Oponn.java:146-162, from the real agents' names when
+ * lux_agent_modelling is on).  agent_ids[p] = ORX_AGENT_* for each of the map's players (orx_state.h; use
+ * orx_agent_from_name on Board.getAgentName(p)); modelling_turn_limit <= 0 or NULL ids switch modelling off (the
+ * state after orx_create).  Takes effect for the rollouts launched after the call; must not be called while a
+ * rollout of this context is in flight. */
+int orx_set_sim_agents(OrxCtx *ctx, const int32_t *agent_ids, int modelling_turn_limit);
 
 /* Text of the last error on this thread (never NULL). */
 const char *orx_last_error(void);

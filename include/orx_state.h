@@ -98,6 +98,46 @@ typedef struct OrxRules {
     int32_t     reserved;
 } OrxRules;
 
+/* ---- opponent modelling ------------------------- */
+
+/* Playout policies = the SimAgent subclasses of src/com/mld46/oponn/sim/agents/ (SimAgent.getSimAgent,
+ * SimAgent.java:248-307).  Every player is SimRandom unless orx_set_sim_agents() says otherwise; with modelling on,
+ * ModellingBoard (ModellingBoard.java:29-47) swaps everybody back to SimRandom at the round wrap where
+ * simTurnCount + 1 == modelling_turn_limit (Oponn.java:55: 2).  Agent names the reference models but this engine does
+ * not yet (cluster, shaft, boscoe, communist, evilpixie, killbot, pixie, quo, yakool) map to ORX_AGENT_RANDOM.
+ *
+ * DECLARED ASSUMPTIONS (Lux SDK not vendored, version unpinned; "parity unpinned" for every modelled policy):
+ *   Country.getNumberEnemyNeighbors()   adjoining countries whose owner differs from this country's owner
+ *   Country.getNumberPlayerNeighbors(p) adjoining countries owned by p;  getNumberNeighbors() = adjoining count
+ *   Country.getWeakestEnemyNeighbor()   the enemy adjoining country with the fewest armies, the first such in
+ *                                       getAdjoiningList() order; null when there is none
+ *   PlayerIterator(p) / ArmiesIterator(p, n) / ContinentIterator(c): countries in code order that are owned by p /
+ *                                       owned by p with armies >= n (n > 0) or <= -n (n < 0) / lie in continent c; the
+ *                                       iterator holds ONE element ahead: next() returns the held element and looks
+ *                                       for the following one in the board as it is at that moment
+ *   BoardHelper.getPlayerArmies(p)      sum of armies on p's countries
+ *   the agents' private `rand` objects  draw from the playout's injected stream like every other draw
+ * Moveable armies: the leaf record does not carry Country.moveableArmies (orx_tree.h keeps them tree-side); a leaf in
+ * FORTIFICATION starts with setupFortificationPhase's values (armies on the current player's countries, else 0). */
+enum { ORX_AGENT_RANDOM = 0, ORX_AGENT_ANGRY = 1, ORX_AGENT_STINKY = 2, ORX_AGENT_COUNT = 3 };
+
+/* SimAgent.getSimAgent(name) (SimAgent.java:248-307): case-insensitive name -> policy id */
+static inline int orx_agent_from_name(const char *name)
+{
+    char b[16]; int i = 0;
+    if (!name) return ORX_AGENT_RANDOM;
+    for (; name[i] && i < 15; i++) b[i] = (char)((name[i] >= 'A' && name[i] <= 'Z') ? name[i] + 32 : name[i]);
+    b[i] = 0;
+    if (name[i]) return ORX_AGENT_RANDOM;
+    if (b[0] == 'a' && b[1] == 'n' && b[2] == 'g' && b[3] == 'r' && b[4] == 'y' && !b[5]) return ORX_AGENT_ANGRY;
+    if (b[0] == 's' && b[1] == 't' && b[2] == 'i' && b[3] == 'n' && b[4] == 'k' && b[5] == 'y' && !b[6]) return ORX_AGENT_STINKY;
+    return ORX_AGENT_RANDOM;
+}
+
+/* engine limit: SimStinky.placeArmies redraws until it hits a border country of its own (SimStinky.java:68-78);
+ * after this many consecutive misses the playout is stopped with ORX_FLAG_STEP_LIMIT */
+#define ORX_MAX_REDRAWS 65536
+
 /* ---- the leaf record (one MCTS leaf = one rollout start state) --------- */
 
 /* Fixed 32-byte header followed by four byte arrays whose offsets depend only on

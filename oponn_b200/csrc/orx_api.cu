@@ -193,7 +193,9 @@ struct OrxCtx {
     DevMap dm;
     int nwt = 2;
     int sm_count = 0;
-    int blocks_per_sm[2] = { 0, 0 };  // [replay]
+    int blocks_per_sm[4] = { 0, 0, 0, 0 };  // [replay + 2 * modelling]
+    bool modelling = false;           // orx_set_sim_agents: the MODEL kernels run, the slice carries moveable armies
+    int blocks_cap = 0;               // ORX_BLOCKS_PER_SM tuning knob
     size_t smem_bytes = 0;
     uint8_t *d_blob = nullptr;
     int32_t *d_bonus_table = nullptr, *d_card_table = nullptr;
@@ -267,12 +269,52 @@ static int32_t java_d2i_host(double d)
     return (int32_t)d;
 }
 
-template <int NWT, bool REPLAY>
-static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm)
+typedef void (*RolloutKernel)(const DevMap, const RolloutArgs);
+
+// the eight instantiations: territories <= 64 or more, counter or replay stream, all-SimRandom or modelled opponents
+static RolloutKernel kernel_for(int nwt, bool replay, bool model)
 {
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<NWT, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (nwt == 2) {
+        if (model) return replay ? rollout_kernel<2, true, true> : rollout_kernel<2, false, true>;
+        return replay ? rollout_kernel<2, true, false> : rollout_kernel<2, false, false>;
+    }
+    if (model) return replay ? rollout_kernel<8, true, true> : rollout_kernel<8, false, true>;
+    return replay ? rollout_kernel<8, true, false> : rollout_kernel<8, false, false>;
+}
+
+static cudaError_t configure_kernel(RolloutKernel k, size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rollout_kernel<NWT, REPLAY>, ORX_BLOCK_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)k, ORX_BLOCK_THREADS, smem);
+}
+
+// per-warp slice of dynamic shared memory; the moveable-armies array only exists while opponent modelling is on
+static void layout_slice(OrxCtx *c, bool with_moveable)
+{
+    DevMap &dm = c->dm;
+    int off = ORX_WARP_HDR_BYTES;
+    dm.w_rng = off;    off += 512;
+    dm.w_armies = off; off += 4 * dm.NP;
+    dm.w_owner = off;  off += dm.NP;
+    dm.w_alist = off;  off += dm.cap;
+    dm.w_cards = off;  off += (dm.P + 1) * dm.cap;
+    off = (off + 3) & ~3;
+    dm.w_move = off;   if (with_moveable) off += 4 * dm.NP;
+    dm.w_bytes = (off + 15) & ~15;
+    c->smem_bytes = (size_t)dm.blob_bytes + (size_t)(ORX_BLOCK_THREADS / 32) * (size_t)dm.w_bytes;
+}
+
+// occupancy of the two kernels (counter / replay) this context launches with its current slice size
+static int configure_context(OrxCtx *c)
+{
+    for (int replay = 0; replay < 2; replay++) {
+        int idx = replay + 2 * (int)c->modelling;
+        CK(configure_kernel(kernel_for(c->nwt, replay != 0, c->modelling), c->smem_bytes, &c->blocks_per_sm[idx]));
+        if (c->blocks_cap >= 1 && c->blocks_per_sm[idx] > c->blocks_cap) c->blocks_per_sm[idx] = c->blocks_cap;
+        if (c->blocks_per_sm[idx] < 1) return set_err(ORX_E_CUDA, "rollout kernel does not fit on an SM");
+    }
+    return ORX_OK;
 }
 
 extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, OrxCtx **out)
@@ -349,15 +391,8 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
     }
     for (int i = 0; i < C; i++) bonus[i] = map->continent_bonus[i];
 
-    // per-warp dynamic slice
-    off = ORX_WARP_HDR_BYTES;
-    dm.w_rng = off;    off += 512;
-    dm.w_armies = off; off += 4 * dm.NP;
-    dm.w_owner = off;  off += dm.NP;
-    dm.w_alist = off;  off += dm.cap;
-    dm.w_cards = off;  off += (P + 1) * dm.cap;
-    dm.w_bytes = (off + 15) & ~15;
-    c->smem_bytes = (size_t)dm.blob_bytes + (size_t)(ORX_BLOCK_THREADS / 32) * (size_t)dm.w_bytes;
+    layout_slice(c, false);
+    dm.model_limit = 0; dm.agents = 0u;
 
     // single-roll thresholds: floor(cdf * 2^53) of O/BattleSim.java:36-44 (float sums widened to double)
     {
@@ -425,18 +460,8 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
         CKC(cudaGetLastError());
         c->launches++;
     }
-    if (c->nwt == 2) {
-        CKC((configure_kernel<2, false>(c->smem_bytes, &c->blocks_per_sm[0])));
-        CKC((configure_kernel<2, true>(c->smem_bytes, &c->blocks_per_sm[1])));
-    } else {
-        CKC((configure_kernel<8, false>(c->smem_bytes, &c->blocks_per_sm[0])));
-        CKC((configure_kernel<8, true>(c->smem_bytes, &c->blocks_per_sm[1])));
-    }
-    if (const char *lim = getenv("ORX_BLOCKS_PER_SM")) {  // tuning knob: cap the resident blocks per SM
-        int v = atoi(lim);
-        if (v >= 1) for (int k = 0; k < 2; k++) if (c->blocks_per_sm[k] > v) c->blocks_per_sm[k] = v;
-    }
-    if (c->blocks_per_sm[0] < 1 || c->blocks_per_sm[1] < 1) { set_err(ORX_E_CUDA, "rollout kernel does not fit on an SM"); orx_destroy(c); return ORX_E_CUDA; }
+    if (const char *lim = getenv("ORX_BLOCKS_PER_SM")) c->blocks_cap = atoi(lim);  // tuning knob: cap the resident blocks per SM
+    if (configure_context(c) != ORX_OK) { orx_destroy(c); return ORX_E_CUDA; }
     CKC(cudaStreamSynchronize(c->stream));
 #undef CKC
     *out = c;
@@ -459,6 +484,31 @@ extern "C" void orx_destroy(OrxCtx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// new ModellingBoard(bs, sas, cm, cid, modellingTurnLimit) (ModellingBoard.java:13-19)
+extern "C" int orx_set_sim_agents(OrxCtx *c, const int32_t *agent_ids, int modelling_turn_limit)
+{
+    if (!c) return set_err(ORX_E_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    for (int k = 0; k < 2; k++) if (c->aslot[k].busy) return set_err(ORX_E_INVALID, "a rollout of this context is in flight");
+    CK(cudaStreamSynchronize(c->stream));
+    uint32_t packed = 0;
+    bool on = agent_ids && modelling_turn_limit > 0;
+    if (on) {
+        bool any = false;
+        for (int p = 0; p < c->dm.P; p++) {
+            if (agent_ids[p] < 0 || agent_ids[p] >= ORX_AGENT_COUNT) return set_err(ORX_E_INVALID, "unknown agent id (see ORX_AGENT_* in orx_state.h)");
+            packed |= (uint32_t)agent_ids[p] << (3 * p);
+            any = any || agent_ids[p] != ORX_AGENT_RANDOM;
+        }
+        on = any;  // an all-SimRandom line-up behind ModellingBoard is the plain board (ModellingBoard.java:29-47)
+    }
+    c->modelling = on;
+    c->dm.agents = on ? packed : 0u;
+    c->dm.model_limit = on ? modelling_turn_limit : 0;
+    layout_slice(c, on);
+    return configure_context(c);
 }
 
 extern "C" int orx_leaf_stride(const OrxCtx *c) { return c ? c->dm.leaf_stride : ORX_E_INVALID; }
@@ -489,27 +539,20 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStr
     const bool timed = stream == nullptr;
     if (!stream) stream = c->stream;
     CK(cudaMemsetAsync(ar.ticket, 0, sizeof(unsigned long long), stream));
-    unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[replay] * (ORX_BLOCK_THREADS / 32);
+    const RolloutKernel kern = kernel_for(c->nwt, replay, c->modelling);
+    unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[(int)replay + 2 * (int)c->modelling] * (ORX_BLOCK_THREADS / 32);
     unsigned long long need = (ar.total + (ORX_BLOCK_THREADS / 32) - 1) / (ORX_BLOCK_THREADS / 32);
     unsigned long long blocks = warps / (ORX_BLOCK_THREADS / 32);
     if (need < blocks) blocks = need;
     if (blocks == 0) blocks = 1;
     // the opt-in shared-memory size is per function, not per context: re-assert it for this context's map
     {
-        int dummy;
-        cudaError_t e = c->nwt == 2 ? (replay ? configure_kernel<2, true>(c->smem_bytes, &dummy) : configure_kernel<2, false>(c->smem_bytes, &dummy))
-                                    : (replay ? configure_kernel<8, true>(c->smem_bytes, &dummy) : configure_kernel<8, false>(c->smem_bytes, &dummy));
-        if (e != cudaSuccess) return set_err(ORX_E_CUDA, "configure_kernel: %s", cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+        if (e != cudaSuccess) return set_err(ORX_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     if (timed) CK(cudaEventRecord(c->ev0, stream));
     dim3 grid((unsigned)blocks), block(ORX_BLOCK_THREADS);
-    if (c->nwt == 2) {
-        if (replay) rollout_kernel<2, true><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
-        else rollout_kernel<2, false><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
-    } else {
-        if (replay) rollout_kernel<8, true><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
-        else rollout_kernel<8, false><<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
-    }
+    kern<<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
     CK(cudaGetLastError());
     if (timed) { CK(cudaEventRecord(c->ev1, stream)); c->have_time = true; }
     c->launches++;

@@ -46,6 +46,9 @@ struct DevMap {
     int32_t bonus_off;          // i32 [C]         initialContinentBonuses
     // per-warp dynamic slice (bytes from the slice base)
     int32_t w_rng, w_armies, w_owner, w_alist, w_cards, w_bytes;
+    int32_t w_move;             // moveable armies (i32 [NP]); only laid out while opponent modelling is on
+    int32_t model_limit;        // ModellingBoard.modellingTurnLimit, 0 = modelling off
+    uint32_t agents;            // ORX_AGENT_* of player p in bits 3p..3p+2
     int32_t leaf_stride, off_owner, off_armies, off_ncards, off_cards;
     int32_t start_armies;       // calculateStartingArmies base (SimulationBoard.java:518-533)
     const uint8_t  *blob;       // global copy of the static map image

@@ -28,12 +28,14 @@ struct RolloutArgs {
     uint32_t words_per_game;
 };
 
-template <int NWT, bool REPLAY>
+template <int NWT, bool REPLAY, bool MODEL = false>
 struct Game {
     const DevMap &dm;
     // 32-bit shared-window addresses: the static map image (per block) and this warp's slice
     saddr s_adj, s_deg, s_sym, s_nbr, s_cont, s_bonus;
     saddr a_arm, a_own, a_alist, a_cards, a_hdr;
+    saddr a_move;             // MODEL: Country.moveableArmies, int32 per territory
+    uint32_t agents;          // MODEL: ORX_AGENT_* of player p in bits 3p..3p+2 (simAgents[], ModellingBoard.java)
     Stream<REPLAY> s;
     int lane;
 
@@ -312,19 +314,30 @@ struct Game {
         }
     }
 
-    // SimRandom.moveArmiesIn (SimRandom.java:144-155) + executeInvasion (:814-825)
-    __device__ __forceinline__ void invade(int A, int D)
+    // SimRandom.moveArmiesIn (SimRandom.java:144-155)
+    __device__ __forceinline__ int random_move_in(int A)
+    {
+        int available = armies(A) - 1;
+        if (available == 0) { fail(); return 0; }
+        int mn = available < 3 ? available : 3;
+        return mn + (mn == available ? 0 : s.next_int(available - mn));
+    }
+    // executeInvasion (:814-825)
+    __device__ __forceinline__ void execute_invasion(int A, int D, int req)
     {
         int aArm = armies(A);
-        int available = aArm - 1;
-        if (available == 0) { fail(); return; }
-        int mn = available < 3 ? available : 3;
-        int req = mn + (mn == available ? 0 : s.next_int(available - mn));
         int lo = aArm - 1 < 3 ? aArm - 1 : 3, hi = aArm - 1;
         int inv = req > lo ? req : lo; if (inv > hi) inv = hi;
         __syncwarp();
         if (lane == 0) { sts32(a_arm + 4u * (uint32_t)D, (uint32_t)inv); sts32(a_arm + 4u * (uint32_t)A, (uint32_t)(aArm - inv)); }
         __syncwarp();
+    }
+    // simAgents[currentPlayer].moveArmiesIn + executeInvasion
+    __device__ __forceinline__ void invade(int A, int D)
+    {
+        int req = MODEL ? sim_move_in(A, D) : random_move_in(A);
+        if (s.flags) return;
+        execute_invasion(A, D, req);
     }
 
     // finishInvasion (:827-841)
@@ -456,6 +469,297 @@ struct Game {
         phase = ORX_PHASE_FORTIFICATION;
     }
 
+
+    // ==================================================================================================
+    // Modelled opponents: SimAngry and SimStinky behind ModellingBoard.  Only the MODEL
+    // instantiations carry this code; the SDK semantics are the DECLARED ASSUMPTIONS of include/orx_state.h.
+    // ==================================================================================================
+    __device__ __forceinline__ int agent_of(int p) const { return MODEL ? (int)((agents >> (3 * p)) & 7u) : (int)ORX_AGENT_RANDOM; }
+    __device__ __forceinline__ int moveable(int t) const { return (int)lds32(a_move + 4u * (uint32_t)t); }
+
+    // Country.getNumberEnemyNeighbors(): adjoining countries whose owner differs from t's owner (one per lane)
+    __device__ __forceinline__ int num_enemy_neighbors(int t) const
+    {
+        const int dg = deg(t), o = owner(t);
+        bool e = false;
+        if (lane < dg) e = owner(adj(t, lane)) != o;
+        return __popc(__ballot_sync(ORX_FULL, e));
+    }
+    // Country.getWeakestEnemyNeighbor(): fewest armies, first in getAdjoiningList() order; -1 = null
+    __device__ __forceinline__ int weakest_enemy_neighbor(int t) const
+    {
+        const int dg = deg(t), o = owner(t);
+        uint32_t key = 0xFFFFFFFFu;
+        int nb = 0;
+        if (lane < dg) { nb = adj(t, lane); if (owner(nb) != o) key = ((uint32_t)armies(nb) << 5) | (uint32_t)lane; }
+        uint32_t best = __reduce_min_sync(ORX_FULL, key);
+        if (best == 0xFFFFFFFFu) return -1;
+        return from_lane(nb, (int)(best & 31u));
+    }
+    // the element a PlayerIterator (arm == 0) / ArmiesIterator(player, arm) holds after looking from `from` on
+    __device__ __forceinline__ int iter_find(int from, int player, int arm) const
+    {
+        int res = -1;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int t = w * 32 + lane;
+            bool ok = t >= from && t < dm.N && owner(t) == player;
+            if (ok && arm != 0) { int a = armies(t); ok = arm > 0 ? a >= arm : a <= -arm; }
+            uint32_t m = __ballot_sync(ORX_FULL, ok);
+            if (res < 0 && m) res = w * 32 + __ffs(m) - 1;
+        }
+        return res;
+    }
+
+    // SimulationBoard.placeArmies (:647-684)
+    __device__ __forceinline__ void place_armies(int n, int t)
+    {
+        bool okphase = phase == ORX_PHASE_PLACEMENT || phase == ORX_PHASE_INITIAL_PLACEMENT ||
+                       (phase == ORX_PHASE_ATTACK && attackState == ORX_ATTACK_PLACE);
+        if (!okphase || n > placeable || n < 0 || owner(t) != cp) { fail(); return; }
+        set_armies(t, armies(t) + n);
+        placeable -= n;
+        if (phase == ORX_PHASE_INITIAL_PLACEMENT && lane == cp) ialp -= n;
+    }
+
+    // SimulationBoard.fortifyArmies (:908-954)
+    __device__ __forceinline__ int fortify_armies(int n, int src, int dst)
+    {
+        if (phase != ORX_PHASE_FORTIFICATION) { fail(); return -1; }
+        if (owner(src) != cp || owner(dst) != cp) return -1;
+        if (n < 0) return -1;
+        int sa = armies(src), mv = moveable(src);
+        int k = mv < sa - 1 ? mv : sa - 1;
+        if (n < k) k = n;
+        if (k == 0) return 0;
+        int da = dst == src ? sa - k : armies(dst);
+        __syncwarp();
+        if (lane == 0) {
+            sts32(a_arm + 4u * (uint32_t)src, (uint32_t)(sa - k)); sts32(a_move + 4u * (uint32_t)src, (uint32_t)(mv - k));
+            sts32(a_arm + 4u * (uint32_t)dst, (uint32_t)(da + k));
+        }
+        __syncwarp();
+        return 1;
+    }
+    // setupFortificationPhase (:900-906)
+    __device__ __forceinline__ void setup_fortification_phase()
+    {
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; sts32(a_move + 4u * (uint32_t)t, owner(t) == cp ? (uint32_t)armies(t) : 0u); }
+        __syncwarp();
+    }
+
+    // SimAngry / SimStinky .moveArmiesIn (SimAngry.java:199-213, SimStinky.java:111-125), else SimRandom's
+    __device__ __forceinline__ int sim_move_in(int A, int D)
+    {
+        const int ag = agent_of(cp);
+        if (ag == ORX_AGENT_ANGRY) {
+            int ae = num_enemy_neighbors(A), de = num_enemy_neighbors(D);
+            return ae > de ? 0 : armies(A) - 1;
+        }
+        if (ag == ORX_AGENT_STINKY) {
+            int aw = weakest_enemy_neighbor(A), dw = weakest_enemy_neighbor(D);
+            if (aw < 0) return 1000000;
+            if (dw < 0) return 0;
+            return armies(aw) < armies(dw) ? 0 : 1000000;
+        }
+        return random_move_in(A);
+    }
+
+    // SimulationBoard.attack(attackingCC, defendingCC, true) (:713-744): 7 conquered, 13 attackers spent, else 0
+    __device__ __forceinline__ int board_attack(int A, int D)
+    {
+        attackUntilDead = 1;
+        int aArm = armies(A), dArm = armies(D), al, dl;
+        simulate_battle(dm, s, aArm - 1, dArm, al, dl);
+        if (s.flags) return 0;
+        aArm -= al; dArm -= dl;
+        __syncwarp();
+        if (lane == 0) { sts32(a_arm + 4u * (uint32_t)A, (uint32_t)aArm); sts32(a_arm + 4u * (uint32_t)D, (uint32_t)dArm); }
+        __syncwarp();
+        if (dArm == 0) {
+            const int ap = owner(A), dp = owner(D);  // setupInvasion (:797-812)
+            if (lane == ap) pc++;
+            if (lane == dp) pc--;
+            set_owner(D, ap);
+            attackingCC = A; defendingCC = D; attackingPlayer = ap; defendingPlayer = dp;
+            int req = sim_move_in(A, D);
+            if (s.flags) return 0;
+            execute_invasion(A, D, req);
+            finish_invasion();
+            return 7;
+        }
+        attackState = ORX_ATTACK_START;
+        return aArm == 1 ? 13 : 0;
+    }
+
+    // MapHelper.getSmallestPositiveEmptyContinent / ...OpenContinent (MapHelper.java:132-191)
+    __device__ __forceinline__ int smallest_positive_continent(const uint32_t (&free_)[NWT], bool need_all) const
+    {
+        int smallestSize = 0x7FFFFFFF, smallest = -1;
+        for (int c = 0; c < dm.C; c++) {
+            int size = 0, un = 0;
+#pragma unroll
+            for (int w = 0; w < NWT; w++) { uint32_t cm = contmask(c, w); size += __popc(cm); un += __popc(cm & free_[w]); }
+            bool ok = need_all ? un == size : un > 0;
+            if (size < smallestSize && ok && current_bonus(c) > 0) { smallestSize = size; smallest = c; }
+        }
+        return smallest;
+    }
+    // SimAngry.pickCountry + pickCountryInContinent (SimAngry.java:49-105)
+    __device__ __forceinline__ int angry_pick_country()
+    {
+        uint32_t free_[NWT], mine[NWT];
+        owned_mask((int)ORX_OWNER_NONE, free_);
+        owned_mask(cp, mine);
+        int goal = smallest_positive_continent(free_, true);
+        if (goal == -1) goal = smallest_positive_continent(free_, false);
+        if (goal == -1) return -1;
+        int res = -1;
+        // an unowned country of the continent that touches one of ours, first in code order
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int t = w * 32 + lane;
+            uint32_t touch = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NWT; w2++) touch |= nbr(w2, t) & mine[w2];
+            bool ok = ((contmask(goal, w) & free_[w]) >> lane) & 1u;
+            uint32_t m = __ballot_sync(ORX_FULL, ok && touch != 0u);
+            if (res < 0 && m) res = w * 32 + __ffs(m) - 1;
+        }
+        if (res >= 0) return res;
+        // else the unowned one with the fewest neighbours, first in code order
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < NWT; w++) {
+            int t = w * 32 + lane;
+            bool ok = ((contmask(goal, w) & free_[w]) >> lane) & 1u;
+            uint32_t key = ok ? ((uint32_t)deg(t) << 8) | (uint32_t)t : 0xFFFFFFFFu;
+            uint32_t k = __reduce_min_sync(ORX_FULL, key);
+            if (k < best) best = k;
+        }
+        return best == 0xFFFFFFFFu ? -1 : (int)(best & 0xFFu);
+    }
+    // SimAngry.placeArmies (SimAngry.java:126-151)
+    __device__ __forceinline__ void angry_place(int n)
+    {
+        int most = -1, placeOn = -1;
+        for (int t = iter_find(0, cp, 0); t >= 0; t = iter_find(t + 1, cp, 0)) {
+            int e = num_enemy_neighbors(t);
+            if (e > most) { most = e; placeOn = t; }
+        }
+        if (placeOn < 0) { fail(); return; }
+        place_armies(n, placeOn);
+    }
+    // SimAngry.attackPhase (SimAngry.java:157-195)
+    __device__ __forceinline__ void angry_attack_phase()
+    {
+        const int me = cp;
+        bool made = true;
+        while (made && !s.flags) {
+            made = false;
+            int held = iter_find(0, me, 2);
+            while (held >= 0 && !s.flags) {
+                int us = held;
+                held = iter_find(us + 1, me, 2);
+                int weak = weakest_enemy_neighbor(us);
+                if (weak >= 0 && armies(us) > armies(weak)) { board_attack(us, weak); made = true; }
+            }
+        }
+    }
+    // SimAngry.fortifyPhase (SimAngry.java:215-279)
+    __device__ __forceinline__ void angry_fortify_phase()
+    {
+        for (int i = 0; i < dm.N && !s.flags; i++) {
+            if (owner(i) != cp || moveable(i) <= 0) continue;
+            const int dg = deg(i);
+            int bestT = -1, bestE = 0;
+            for (int j = 0; j < dg; j++) {
+                int nb = adj(i, j);
+                if (owner(nb) == cp) { int e = num_enemy_neighbors(nb); if (e > bestE) { bestT = nb; bestE = e; } }
+            }
+            int e = num_enemy_neighbors(i);
+            if (bestE > e) {
+                fortify_armies(moveable(i), i, bestT);
+            } else if (e == 0) {
+                int r = s.next_int(dg);  // nextInt(0) throws
+                if (s.flags) return;
+                fortify_armies(moveable(i), i, adj(i, r));
+            }
+        }
+    }
+    // SimStinky.placeArmies (SimStinky.java:66-78)
+    __device__ __forceinline__ void stinky_place(int n)
+    {
+        int test, tries = 0;
+        for (;;) {
+            if (tries++ >= ORX_MAX_REDRAWS) { s.flags |= ORX_FLAG_STEP_LIMIT; return; }  // engine limit
+            test = s.next_int(dm.N);
+            if (s.flags) return;
+            if (owner(test) == cp && num_enemy_neighbors(test) > 0) break;
+        }
+        place_armies(n, test);
+    }
+    // SimStinky.attackPhase(boolean) (SimStinky.java:91-109); armies > weak * 1.5 <=> 2 * armies > 3 * weak
+    __device__ __forceinline__ bool stinky_attack_pass(bool care)
+    {
+        const int me = cp;
+        bool attacked = false;
+        int held = iter_find(0, me, 0);
+        while (held >= 0 && !s.flags) {
+            int us = held;
+            held = iter_find(us + 1, me, 0);
+            int weak = weakest_enemy_neighbor(us);
+            if (weak >= 0) {
+                long long a = armies(us), w = armies(weak);
+                if (a > 1 && (!care || 2 * a > 3 * w)) { board_attack(us, weak); attacked = true; }
+            }
+        }
+        return attacked;
+    }
+    // SimStinky.attackPhase() (SimStinky.java:80-89)
+    __device__ __forceinline__ void stinky_attack_phase()
+    {
+        stinky_attack_pass(true);
+        if (s.flags) return;
+        int mysum = 0;  // BoardHelper.getPlayerArmies
+#pragma unroll
+        for (int w = 0; w < NWT; w++) { int t = w * 32 + lane; if (t < dm.N && owner(t) == cp) mysum += armies(t); }
+        int total = (int)__reduce_add_sync(ORX_FULL, (unsigned)mysum);
+        if (total > 300)
+            while (!s.flags && stinky_attack_pass(false)) { }
+    }
+
+    // simAgents[currentPlayer].xxx()
+    __device__ __forceinline__ void sim_place(int n)
+    {
+        if (MODEL) {
+            const int ag = agent_of(cp);
+            if (ag == ORX_AGENT_ANGRY) { angry_place(n); return; }
+            if (ag == ORX_AGENT_STINKY) { stinky_place(n); return; }
+        }
+        agent_place(n);
+    }
+    __device__ __forceinline__ void sim_cards_phase()
+    {
+        if (MODEL && agent_of(cp) != ORX_AGENT_RANDOM) return;  // SimAngry / SimStinky: empty
+        agent_cards_phase();
+    }
+    __device__ __forceinline__ void sim_attack_phase()
+    {
+        if (MODEL) {
+            const int ag = agent_of(cp);
+            if (ag == ORX_AGENT_ANGRY) { angry_attack_phase(); return; }
+            if (ag == ORX_AGENT_STINKY) { stinky_attack_phase(); return; }
+        }
+        agent_attack_phase();
+    }
+    __device__ __forceinline__ void sim_fortify_phase()
+    {
+        if (MODEL && agent_of(cp) == ORX_AGENT_ANGRY) angry_fortify_phase();  // SimRandom, SimStinky: empty
+    }
+
     // ---- fortification / turn advance -------------------------------------------------
     // checkForOverflow (:984-1015)
     __device__ __forceinline__ void check_for_overflow()
@@ -484,6 +788,7 @@ struct Game {
         if (alive == 0u) { fail(); return; }  // the reference would spin forever
         uint32_t above = alive & ~((2u << cp) - 1u);
         int np = above ? __ffs(above) - 1 : __ffs(alive) - 1;
+        if (MODEL && np < cp && simTurn + 1 == dm.model_limit) agents = 0u;  // ModellingBoard.java:29-47: all SimRandom
         if (np < cp) { simTurn++; recalculate_bonuses(); }
         cp = np;
         phase = ORX_PHASE_CARDS;
@@ -503,12 +808,20 @@ struct Game {
     }
     __device__ __forceinline__ void select_country()
     {
-        uint32_t free_[NWT];
-        owned_mask((int)ORX_OWNER_NONE, free_);
-        int n = count_bits(free_);
-        int i = s.next_int(n);  // nextInt(0) throws
-        if (s.flags) return;
-        int cc = nth_territory(free_, i);
+        int cc;
+        if (MODEL && agent_of(cp) == ORX_AGENT_ANGRY) {
+            cc = angry_pick_country();
+        } else if (MODEL && agent_of(cp) == ORX_AGENT_STINKY) {
+            cc = -1;  // SimStinky.pickCountry (SimStinky.java:51-54); selectCountry then indexes countries[-1]
+        } else {
+            uint32_t free_[NWT];
+            owned_mask((int)ORX_OWNER_NONE, free_);
+            int n = count_bits(free_);
+            int i = s.next_int(n);  // nextInt(0) throws
+            if (s.flags) return;
+            cc = nth_territory(free_, i);
+        }
+        if (cc < 0 || owner(cc) != (int)ORX_OWNER_NONE) { fail(); return; }  // selectCountry (:485-494)
         set_owner(cc, cp);
         if (lane == cp) { pc++; ialp--; }
         set_hdr(WH_REM_COUNTRIES, hdr(WH_REM_COUNTRIES) - 1u);
@@ -582,6 +895,17 @@ struct Game {
         __syncwarp();
         if (bad || __any_sync(ORX_FULL, badt)) { fail(); return; }
 
+        if (MODEL) {
+            // simAgents = initialSimAgents (ModellingBoard.java:21-27); moveableArmies are not in the record: a
+            // FORTIFICATION leaf starts from setupFortificationPhase's values (orx_state.h)
+            agents = dm.agents;
+#pragma unroll
+            for (int w = 0; w < NWT; w++) {
+                int t = w * 32 + lane;
+                sts32(a_move + 4u * (uint32_t)t, (h_phase == ORX_PHASE_FORTIFICATION && owner(t) == h_cp) ? (uint32_t)armies(t) : 0u);
+            }
+            __syncwarp();
+        }
         cp = h_cp; phase = h_phase; simTurn = 0; cardpos = h_cardpos;
         placeable = 0; hasInvaded = 0; playerTurns = 0;
         attackState = ORX_ATTACK_START; attackingCC = defendingCC = attackingPlayer = defendingPlayer = -1;
@@ -676,18 +1000,18 @@ struct Game {
                 break;
             case ORX_PHASE_INITIAL_PLACEMENT:
                 if (!first) setup_initial_placement_phase();
-                agent_place(placeable);
+                if (!(MODEL && first && placeable <= 0)) sim_place(placeable);  // catch-up: only when there is something to place
                 tear_down_initial_placement_phase();
                 if (!first) step_limit_hit();
                 break;
             case ORX_PHASE_CARDS:
                 if (!first) placeable = 0;  // setupCardsPhase (:572-575)
-                agent_cards_phase();
+                sim_cards_phase();
                 tear_down_cards_phase();
                 break;
             case ORX_PHASE_PLACEMENT:
                 if (!first) placeable = (int)((uint32_t)placeable + (uint32_t)player_income());  // setupPlacementPhase
-                agent_place(placeable);
+                if (!(MODEL && first && placeable <= 0)) sim_place(placeable);
                 phase = ORX_PHASE_ATTACK;  // tearDownPlacementPhase (:686-694)
                 break;
             case ORX_PHASE_ATTACK:
@@ -715,20 +1039,25 @@ struct Game {
                     }
                     if (attackState == ORX_ATTACK_CASH) {  // executeAttackCash (:869-876)
                         placeable = 0;
-                        agent_cards_phase();
+                        sim_cards_phase();
                         attackState = ORX_ATTACK_PLACE;
                         if (s.flags) break;
                     }
                     if (attackState == ORX_ATTACK_PLACE) {  // executeAttackPlacement (:878-882)
-                        agent_place(placeable);
+                        sim_place(placeable);
                         attackState = ORX_ATTACK_START;
                         if (s.flags) break;
                     }
                 }
-                agent_attack_phase();
+                sim_attack_phase();
                 if (!s.flags) tear_down_attack_phase();
                 break;
             default:  // FORTIFICATION: SimRandom.fortifyPhase is a no-op (SimRandom.java:158-160)
+                if (MODEL) {
+                    if (!first) setup_fortification_phase();
+                    sim_fortify_phase();
+                    if (s.flags) break;
+                }
                 tear_down_fortification_phase();
                 if (!first) step_limit_hit();
                 break;
@@ -773,7 +1102,7 @@ struct Game {
 };
 
 // The rollout kernel: persistent warps pull game indices from a ticket counter.
-template <int NWT, bool REPLAY>
+template <int NWT, bool REPLAY, bool MODEL>
 __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ RolloutArgs ar)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -787,7 +1116,7 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
     const int wid = __shfl_sync(ORX_FULL, (int)(threadIdx.x >> 5), 0);
     uint8_t *slice = smem + dm.blob_bytes + wid * dm.w_bytes;
 
-    Game<NWT, REPLAY> g(dm);
+    Game<NWT, REPLAY, MODEL> g(dm);
     // pinned in registers: without the barrier ptxas re-derives the shared window base inside the hot loops
     saddr sbase = to_saddr(smem), wbase = to_saddr(slice);
     asm volatile("" : "+r"(sbase), "+r"(wbase));
@@ -797,6 +1126,7 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
     g.a_hdr = wbase;
     g.a_arm = wbase + (uint32_t)dm.w_armies; g.a_own = wbase + (uint32_t)dm.w_owner;
     g.a_alist = wbase + (uint32_t)dm.w_alist; g.a_cards = wbase + (uint32_t)dm.w_cards;
+    g.a_move = wbase + (uint32_t)dm.w_move; g.agents = 0u;
     const saddr rng = wbase + (uint32_t)dm.w_rng;
 
     for (;;) {

@@ -73,6 +73,7 @@ def load_library():
     L.orx_stream_draws.argtypes = [vp, u64, u64, vp, u32, vp, C.c_int, vp, p(u32), p(u32)]
     L.orx_stream_draws.restype = C.c_int
     L.orx_card_cash_value.argtypes = [vp, C.c_int, p(i32)]; L.orx_card_cash_value.restype = C.c_int
+    L.orx_set_sim_agents.argtypes = [vp, p(i32), C.c_int]; L.orx_set_sim_agents.restype = C.c_int
     _lib = L
     return L
 
@@ -81,7 +82,7 @@ def load_library():
 EXPORTS = ("orx_create", "orx_destroy", "orx_last_error", "orx_leaf_stride", "orx_rollout_batch",
            "orx_rollout_batch_device", "orx_rollout_begin", "orx_rollout_end", "orx_rollout_replay", "orx_sync", "orx_stream", "orx_last_kernel_ms",
            "orx_kernel_launches", "orx_get_attack_outcomes", "orx_simulate_battles", "orx_simulate_individual",
-           "orx_stream_draws", "orx_card_cash_value")
+           "orx_stream_draws", "orx_card_cash_value", "orx_set_sim_agents")
 
 
 class RolloutEngine:
@@ -89,7 +90,8 @@ class RolloutEngine:
 
     Replaces ``new ModellingBoard(...) x CORES`` (src/com/mld46/oponn/Oponn.java:106-110)."""
 
-    def __init__(self, risk_map: RiskMap, rules: Optional[Rules] = None, device: int = 0):
+    def __init__(self, risk_map: RiskMap, rules: Optional[Rules] = None, device: int = 0,
+                 sim_agents: Optional[Sequence[int]] = None, modelling_turn_limit: int = 2):
         self._h = None
         self._L = load_library()
         self.map, self.rules, self.device = risk_map, rules or Rules(), device
@@ -101,6 +103,20 @@ class RolloutEngine:
         self._h = h
         self.layout = leaf_layout(risk_map.n_territories, risk_map.n_players)
         assert self._L.orx_leaf_stride(self._h) == self.layout.stride
+        if sim_agents is not None:
+            self.set_sim_agents(sim_agents, modelling_turn_limit)
+
+    def set_sim_agents(self, sim_agents: Optional[Sequence[int]], modelling_turn_limit: int = 2):
+        """The ``SimAgent[] sas`` and ``modellingTurnLimit`` of ``new ModellingBoard(bs, sas, cm, cid, limit)``
+        (ModellingBoard.java:13-19; Oponn.createSimAgents, Oponn.java:146-162): one ``state.AGENT_*`` id per player
+        (``state.agent_from_name`` maps Lux agent names); ``None`` switches opponent modelling off."""
+        if sim_agents is None:
+            self._ck(self._L.orx_set_sim_agents(self._h, None, 0))
+            return
+        ids = np.asarray(list(sim_agents), dtype=np.int32)
+        if len(ids) != self.map.n_players:
+            raise ValueError("one agent id per player")
+        self._ck(self._L.orx_set_sim_agents(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), int(modelling_turn_limit)))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self):

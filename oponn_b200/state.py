@@ -27,6 +27,15 @@ ATTACK_START, ATTACK_EXECUTE, ATTACK_INVADE, ATTACK_CASH, ATTACK_PLACE = range(5
 
 FLAG_ERROR, FLAG_STEP_LIMIT, FLAG_STREAM_END = 1, 2, 4
 
+# playout policies (orx_state.h ORX_AGENT_*): the SimAgent subclasses this engine models (SimAgent.java:248-307)
+AGENT_RANDOM, AGENT_ANGRY, AGENT_STINKY = range(3)
+MODELLING_TURN_LIMIT = 2            # Oponn.java:55
+
+
+def agent_from_name(name: str) -> int:
+    """SimAgent.getSimAgent(name): case-insensitive; agents not modelled here play as SimRandom."""
+    return {"angry": AGENT_ANGRY, "stinky": AGENT_STINKY}.get((name or "").lower(), AGENT_RANDOM)
+
 HEADER_BYTES = 32
 
 

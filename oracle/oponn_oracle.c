@@ -599,6 +599,11 @@ typedef struct Board {
     int hasInvadedACountry, attackingCC, defendingCC, attackingPlayer, defendingPlayer;
     int attackUntilDead, attackerLosses, defenderLosses, attackState;
 
+    /* opponent modelling (ModellingBoard.java, SimAgent.java:248-307): policy id per player */
+    int simAgentInitial[MAXP], simAgent[MAXP];
+    int modellingTurnLimit;
+    int moveable[MAXN];       /* Country.getMoveableArmies */
+
     /* engine bookkeeping */
     Stream rng;
     uint32_t flags;
@@ -677,6 +682,7 @@ static void setupGeneralGameState(Board *b)
 {
     b->remainingPlayers = 0;
     b->simTurnCount = 0;
+    for (int p = 0; p < b->P; p++) b->simAgent[p] = b->simAgentInitial[p]; /* ModellingBoard.java:21-27 */
     for (int p = 0; p < b->P; p++) {
         b->playerOutOnTurn[p] = 0;
         b->playerCountries[p] = 0;
@@ -911,6 +917,8 @@ static void finishInvasion(Board *b)
     b->attackingCC = -1; b->defendingCC = -1; b->attackingPlayer = -1; b->defendingPlayer = -1;
 }
 
+static int sim_moveArmiesIn(Board *b, int attackerCC, int defenderCC);
+
 /* SimulationBoard.attack (SimulationBoard.java:713-744), attackState never becomes CASH
  * because the immediateCash branch is commented out (:852-855) */
 static int board_attack(Board *b, int attackingCC, int defendingCC, int attackUntilDead)
@@ -927,7 +935,7 @@ static int board_attack(Board *b, int attackingCC, int defendingCC, int attackUn
     b->ct.attacks++;
     if (b->attackState == ORX_ATTACK_INVADE) {
         setupInvasion(b);
-        executeInvasion(b, agent_moveArmiesIn(b, attackingCC, defendingCC));
+        executeInvasion(b, sim_moveArmiesIn(b, attackingCC, defendingCC));
         finishInvasion(b);
         return 7;
     }
@@ -1014,6 +1022,11 @@ static void tearDownFortificationPhase(Board *b)
     int nextPlayer = b->currentPlayer; /* getNextPlayer :1102-1111 */
     int guard = 0;
     do { nextPlayer = (nextPlayer + 1) % b->P; if (++guard > b->P) { FAIL(b); return; } } while (b->playerCountries[nextPlayer] == 0);
+    /* ModellingBoard.tearDownFortificationPhase (ModellingBoard.java:29-47): everybody becomes SimRandom when the
+     * round that is about to start is round `modellingTurnLimit` */
+    if (nextPlayer < b->currentPlayer && b->simTurnCount + 1 == b->modellingTurnLimit)
+        for (int p = 0; p < b->P; p++) b->simAgent[p] = ORX_AGENT_RANDOM;
+    for (int c = 0; c < b->N; c++) b->moveable[c] = 0;
     if (nextPlayer < b->currentPlayer) { b->simTurnCount++; recalculateContinentBonuses(b); }
     b->currentPlayer = nextPlayer;
     b->currentPhase = ORX_PHASE_CARDS;
@@ -1064,6 +1077,264 @@ static int agent_pickCountry(Board *b)
     return cand[i];
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* Modelled opponents: SimAngry, SimStinky behind ModellingBoard.  */
+/* SDK semantics are DECLARED ASSUMPTIONS (include/orx_state.h): parity unpinned.       */
+/* ------------------------------------------------------------------------------------ */
+
+/* Country.getNumberEnemyNeighbors / getNumberPlayerNeighbors / getWeakestEnemyNeighbor (declared assumptions) */
+static int numEnemyNeighbors(Board *b, int cc)
+{
+    int n = 0;
+    for (int e = b->adj_off[cc]; e < b->adj_off[cc + 1]; e++) { b->ct.ev++; if (b->owner[b->adj[e]] != b->owner[cc]) n++; }
+    return n;
+}
+static int numPlayerNeighbors(Board *b, int cc, int player)
+{
+    int n = 0;
+    for (int e = b->adj_off[cc]; e < b->adj_off[cc + 1]; e++) { b->ct.ev++; if (b->owner[b->adj[e]] == player) n++; }
+    return n;
+}
+static int weakestEnemyNeighbor(Board *b, int cc)
+{
+    int weakest = -1, weakestArmies = 0;
+    for (int e = b->adj_off[cc]; e < b->adj_off[cc + 1]; e++) {
+        int nb = b->adj[e];
+        b->ct.ev++;
+        if (b->owner[nb] != b->owner[cc] && (weakest < 0 || b->armies[nb] < weakestArmies)) { weakest = nb; weakestArmies = b->armies[nb]; }
+    }
+    return weakest;
+}
+/* the element a PlayerIterator (armies == 0) / ArmiesIterator holds after looking from `from` on */
+static int iterFind(Board *b, int from, int player, int armies)
+{
+    for (int cc = from; cc < b->N; cc++) {
+        b->ct.tv++;
+        if (b->owner[cc] != player) continue;
+        if (armies > 0 && b->armies[cc] < armies) continue;
+        if (armies < 0 && b->armies[cc] > -armies) continue;
+        return cc;
+    }
+    return -1;
+}
+
+/* SimulationBoard.fortifyArmies (SimulationBoard.java:908-954) */
+static int fortifyArmies(Board *b, int numberOfArmies, int sourceCC, int destinationCC)
+{
+    if (b->currentPhase != ORX_PHASE_FORTIFICATION) { FAIL(b); return -1; }
+    if (b->owner[sourceCC] != b->currentPlayer || b->owner[destinationCC] != b->currentPlayer) return -1;
+    if (numberOfArmies < 0) return -1;
+    int sourceArmies = b->armies[sourceCC], moveableArmies = b->moveable[sourceCC];
+    int armiesToFortify = moveableArmies < sourceArmies - 1 ? moveableArmies : sourceArmies - 1;
+    if (numberOfArmies < armiesToFortify) armiesToFortify = numberOfArmies;
+    if (armiesToFortify == 0) return 0;
+    b->armies[sourceCC] = sourceArmies - armiesToFortify;
+    b->moveable[sourceCC] = moveableArmies - armiesToFortify;
+    b->armies[destinationCC] += armiesToFortify;
+    b->ct.writes += 3;
+    return 1;
+}
+
+/* SimulationBoard.setupFortificationPhase (:900-906) */
+static void setupFortificationPhase(Board *b)
+{
+    for (int c = 0; c < b->N; c++) b->moveable[c] = b->owner[c] == b->currentPlayer ? b->armies[c] : 0;
+}
+
+/* MapHelper.getSmallestPositiveEmptyContinent / getSmallestPositiveOpenContinent (MapHelper.java:132-191):
+ * empty = every country of the continent unowned, open = at least one unowned */
+static int smallestPositiveContinent(Board *b, int needAll)
+{
+    int smallestSize = 2147483647, smallestContinent = -1;
+    for (int continent = 0; continent < b->C; continent++) {
+        int size = 0, unowned = 0;
+        for (int cc = 0; cc < b->N; cc++) { b->ct.tv++; if (b->continent[cc] == continent) { size++; if (b->owner[cc] == -1) unowned++; } }
+        int ok = needAll ? unowned == size : unowned > 0;
+        if (size < smallestSize && ok && b->currentContinentBonuses[continent] > 0) { smallestSize = size; smallestContinent = continent; }
+    }
+    return smallestContinent;
+}
+
+/* SimAngry.pickCountry + pickCountryInContinent (SimAngry.java:49-105) */
+static int angry_pickCountry(Board *b)
+{
+    int ID = b->currentPlayer;
+    int goalCont = smallestPositiveContinent(b, 1);
+    if (goalCont == -1) goalCont = smallestPositiveContinent(b, 0);
+    for (int cc = 0; cc < b->N; cc++) {
+        b->ct.tv++;
+        if (b->continent[cc] == goalCont && b->owner[cc] == -1 && numPlayerNeighbors(b, cc, ID) > 0) return cc;
+    }
+    int bestCode = -1, fewestNeib = 1000000;
+    for (int cc = 0; cc < b->N; cc++) {
+        b->ct.tv++;
+        int nn = b->adj_off[cc + 1] - b->adj_off[cc];
+        if (b->continent[cc] == goalCont && b->owner[cc] == -1 && nn < fewestNeib) { bestCode = cc; fewestNeib = nn; }
+    }
+    return bestCode; /* -1: selectCountry indexes countries[-1] and throws */
+}
+
+/* SimAngry.placeArmies (SimAngry.java:126-151): everything on the owned country with the most enemy neighbours */
+static void angry_placeArmies(Board *b, int numberOfArmies)
+{
+    int ID = b->currentPlayer, mostEnemies = -1, placeOn = -1;
+    for (int cc = iterFind(b, 0, ID, 0); cc >= 0; cc = iterFind(b, cc + 1, ID, 0)) {
+        int subTotalEnemies = numEnemyNeighbors(b, cc);
+        if (subTotalEnemies > mostEnemies) { mostEnemies = subTotalEnemies; placeOn = cc; }
+    }
+    if (placeOn < 0) { FAIL(b); return; } /* placeOn.getCode() on null */
+    placeArmies(b, numberOfArmies, placeOn);
+}
+
+/* SimAngry.attackPhase (SimAngry.java:157-195) */
+static void angry_attackPhase(Board *b)
+{
+    int ID = b->currentPlayer, madeAttack = 1;
+    while (madeAttack && !b->flags) {
+        madeAttack = 0;
+        int held = iterFind(b, 0, ID, 2);
+        while (held >= 0 && !b->flags) {
+            int us = held;
+            held = iterFind(b, us + 1, ID, 2);
+            int weakestNeighbor = weakestEnemyNeighbor(b, us);
+            if (weakestNeighbor >= 0 && b->armies[us] > b->armies[weakestNeighbor]) {
+                board_attack(b, us, weakestNeighbor, 1);
+                madeAttack = 1;
+            }
+        }
+    }
+}
+
+/* SimAngry.moveArmiesIn (SimAngry.java:199-213) */
+static int angry_moveArmiesIn(Board *b, int cca, int ccd)
+{
+    int Aenemies = numEnemyNeighbors(b, cca), Denemies = numEnemyNeighbors(b, ccd);
+    if (Aenemies > Denemies) return 0;
+    return b->armies[cca] - 1;
+}
+
+/* SimAngry.fortifyPhase (SimAngry.java:215-279) */
+static void angry_fortifyPhase(Board *b)
+{
+    int ID = b->currentPlayer;
+    for (int i = 0; i < b->N && !b->flags; i++) {
+        b->ct.tv++;
+        if (b->owner[i] != ID || b->moveable[i] <= 0) continue;
+        int countryCodeBestProspect = -1, bestEnemyNeighbors = 0;
+        for (int e = b->adj_off[i]; e < b->adj_off[i + 1]; e++) {
+            int nb = b->adj[e];
+            if (b->owner[nb] == ID) {
+                int enemyNeighbors = numEnemyNeighbors(b, nb);
+                if (enemyNeighbors > bestEnemyNeighbors) { countryCodeBestProspect = nb; bestEnemyNeighbors = enemyNeighbors; }
+            }
+        }
+        int enemyNeighbors = numEnemyNeighbors(b, i);
+        if (bestEnemyNeighbors > enemyNeighbors) {
+            fortifyArmies(b, b->moveable[i], i, countryCodeBestProspect);
+        } else if (enemyNeighbors == 0) {
+            int nn = b->adj_off[i + 1] - b->adj_off[i];
+            int randCC = jr_next_int(&b->rng, nn); /* nextInt(0) throws */
+            if (b->flags) return;
+            fortifyArmies(b, b->moveable[i], i, b->adj[b->adj_off[i] + randCC]);
+        }
+    }
+}
+
+/* SimStinky.placeArmies (SimStinky.java:66-78) */
+static void stinky_placeArmies(Board *b, int numberOfArmies)
+{
+    int ID = b->currentPlayer, test, tries = 0;
+    do {
+        if (tries++ >= ORX_MAX_REDRAWS) { b->flags |= ORX_FLAG_STEP_LIMIT; return; } /* engine limit */
+        test = jr_next_int(&b->rng, b->N);
+        if (b->flags) return;
+    } while (b->owner[test] != ID || weakestEnemyNeighbor(b, test) < 0);
+    placeArmies(b, numberOfArmies, test);
+}
+
+/* SimStinky.attackPhase(boolean) (SimStinky.java:91-109) */
+static int stinky_attackPass(Board *b, int careAboutOdds)
+{
+    int ID = b->currentPlayer, attacked = 0;
+    int held = iterFind(b, 0, ID, 0);
+    while (held >= 0 && !b->flags) {
+        int us = held;
+        held = iterFind(b, us + 1, ID, 0);
+        int weak = weakestEnemyNeighbor(b, us);
+        if (weak >= 0 && b->armies[us] > 1 && ((double)b->armies[us] > b->armies[weak] * 1.5 || !careAboutOdds)) {
+            board_attack(b, us, weak, 1);
+            attacked = 1;
+        }
+    }
+    return attacked;
+}
+
+/* SimStinky.attackPhase() (SimStinky.java:80-89) */
+static void stinky_attackPhase(Board *b)
+{
+    stinky_attackPass(b, 1);
+    if (b->flags) return;
+    int ID = b->currentPlayer, total = 0; /* BoardHelper.getPlayerArmies */
+    for (int cc = 0; cc < b->N; cc++) { b->ct.tv++; if (b->owner[cc] == ID) total += b->armies[cc]; }
+    if (total > 300)
+        while (!b->flags && stinky_attackPass(b, 0)) { }
+}
+
+/* SimStinky.moveArmiesIn (SimStinky.java:111-125) */
+static int stinky_moveArmiesIn(Board *b, int cca, int ccd)
+{
+    int attackWeak = weakestEnemyNeighbor(b, cca), defendWeak = weakestEnemyNeighbor(b, ccd);
+    if (attackWeak < 0) return 1000000;
+    if (defendWeak < 0) return 0;
+    if (b->armies[attackWeak] < b->armies[defendWeak]) return 0;
+    return 1000000;
+}
+
+/* ---- simAgents[currentPlayer].xxx() ------------------------------------------------ */
+static int sim_agent(const Board *b) { return b->simAgent[b->currentPlayer]; }
+
+static int sim_pickCountry(Board *b)
+{
+    switch (sim_agent(b)) {
+    case ORX_AGENT_ANGRY: return angry_pickCountry(b);
+    case ORX_AGENT_STINKY: return -1; /* "the world will give us a random unowned country" -- this board throws instead */
+    default: return agent_pickCountry(b);
+    }
+}
+static void sim_placeArmies(Board *b, int n) /* placeInitialArmies delegates to it in all three agents */
+{
+    switch (sim_agent(b)) {
+    case ORX_AGENT_ANGRY: angry_placeArmies(b, n); break;
+    case ORX_AGENT_STINKY: stinky_placeArmies(b, n); break;
+    default: agent_place(b, n);
+    }
+}
+static void sim_cardsPhase(Board *b)
+{
+    if (sim_agent(b) == ORX_AGENT_RANDOM) agent_cardsPhase(b); /* SimAngry / SimStinky: empty (tearDownCardsPhase cashes above 4) */
+}
+static void sim_attackPhase(Board *b)
+{
+    switch (sim_agent(b)) {
+    case ORX_AGENT_ANGRY: angry_attackPhase(b); break;
+    case ORX_AGENT_STINKY: stinky_attackPhase(b); break;
+    default: agent_attackPhase(b);
+    }
+}
+static int sim_moveArmiesIn(Board *b, int attackerCC, int defenderCC)
+{
+    switch (sim_agent(b)) {
+    case ORX_AGENT_ANGRY: return angry_moveArmiesIn(b, attackerCC, defenderCC);
+    case ORX_AGENT_STINKY: return stinky_moveArmiesIn(b, attackerCC, defenderCC);
+    default: return agent_moveArmiesIn(b, attackerCC, defenderCC);
+    }
+}
+static void sim_fortifyPhase(Board *b)
+{
+    if (sim_agent(b) == ORX_AGENT_ANGRY) angry_fortifyPhase(b); /* SimRandom, SimStinky: empty */
+}
+
 /* SimulationBoard.setupState (SimulationBoard.java:178-190) from a packed leaf record */
 static void setupState(Board *b, const uint8_t *leaf)
 {
@@ -1098,6 +1369,9 @@ static void setupState(Board *b, const uint8_t *leaf)
 
     /* setupCountries :192-203 */
     for (int cc = 0; cc < b->N; cc++) { b->owner[cc] = owner[cc] == ORX_OWNER_NONE ? -1 : owner[cc]; b->armies[cc] = armies[cc]; }
+    /* moveableArmies are not in the record: setupFortificationPhase's values for a FORTIFICATION leaf, else 0 (orx_state.h) */
+    for (int cc = 0; cc < b->N; cc++)
+        b->moveable[cc] = (h->phase == ORX_PHASE_FORTIFICATION && b->owner[cc] == h->current_player) ? b->armies[cc] : 0;
 
     /* setupCardState :205-227 ; CardManager.simReset :240-248 */
     b->simDeck.n = 0;
@@ -1188,15 +1462,15 @@ static void simulate(Board *b)
         tearDownCountrySelectionPhase(b);
         break;
     case ORX_PHASE_INITIAL_PLACEMENT:
-        if (b->numberOfPlaceableArmies > 0) agent_place(b, b->numberOfPlaceableArmies);
+        if (b->numberOfPlaceableArmies > 0) sim_placeArmies(b, b->numberOfPlaceableArmies);
         tearDownInitialPlacementPhase(b);
         break;
     case ORX_PHASE_CARDS:
-        agent_cardsPhase(b);
+        sim_cardsPhase(b);
         tearDownCardsPhase(b);
         break;
     case ORX_PHASE_PLACEMENT:
-        if (b->numberOfPlaceableArmies > 0) agent_place(b, b->numberOfPlaceableArmies);
+        if (b->numberOfPlaceableArmies > 0) sim_placeArmies(b, b->numberOfPlaceableArmies);
         b->currentPhase = ORX_PHASE_ATTACK; /* tearDownPlacementPhase :686-694 */
         break;
     case ORX_PHASE_ATTACK:
@@ -1204,22 +1478,23 @@ static void simulate(Board *b)
         if (!b->flags && b->attackState == ORX_ATTACK_INVADE) {
             /* no setupInvasion() here: SURVEY 8.1 quirk 1 */
             if (b->attackingCC < 0 || b->defendingCC < 0) { FAIL(b); break; }
-            executeInvasion(b, agent_moveArmiesIn(b, b->attackingCC, b->defendingCC));
+            executeInvasion(b, sim_moveArmiesIn(b, b->attackingCC, b->defendingCC));
             if (!b->flags) finishInvasion(b);
         }
         if (!b->flags && b->attackState == ORX_ATTACK_CASH) { /* executeAttackCash :869-876 */
             b->numberOfPlaceableArmies = 0;
-            agent_cardsPhase(b);
+            sim_cardsPhase(b);
             b->attackState = ORX_ATTACK_PLACE;
         }
         if (!b->flags && b->attackState == ORX_ATTACK_PLACE) { /* executeAttackPlacement :878-882 */
-            agent_place(b, b->numberOfPlaceableArmies);
+            sim_placeArmies(b, b->numberOfPlaceableArmies);
             b->attackState = ORX_ATTACK_START;
         }
-        if (!b->flags) { agent_attackPhase(b); if (!b->flags) tearDownAttackPhase(b); }
+        if (!b->flags) { sim_attackPhase(b); if (!b->flags) tearDownAttackPhase(b); }
         break;
     case ORX_PHASE_FORTIFICATION:
-        tearDownFortificationPhase(b); /* SimRandom.fortifyPhase is a no-op (SimRandom.java:158-160) */
+        sim_fortifyPhase(b); /* SimRandom.fortifyPhase is a no-op (SimRandom.java:158-160) */
+        if (!b->flags) tearDownFortificationPhase(b);
         break;
     default:
         FAIL(b);
@@ -1229,33 +1504,35 @@ static void simulate(Board *b)
     while (b->remainingPlayers > 1 && !b->flags) {
         switch (b->currentPhase) {
         case ORX_PHASE_COUNTRY_SELECTION:
-            selectCountry(b, agent_pickCountry(b));
+            selectCountry(b, sim_pickCountry(b));
             tearDownCountrySelectionPhase(b);
             break;
         case ORX_PHASE_INITIAL_PLACEMENT:
             setupInitialPlacementPhase(b);
-            agent_place(b, b->numberOfPlaceableArmies);
+            sim_placeArmies(b, b->numberOfPlaceableArmies);
             tearDownInitialPlacementPhase(b);
             step_limit_hit(b);
             break;
         case ORX_PHASE_CARDS:
             b->numberOfPlaceableArmies = 0; /* setupCardsPhase :572-575 */
-            agent_cardsPhase(b);
+            sim_cardsPhase(b);
             tearDownCardsPhase(b);
             break;
         case ORX_PHASE_PLACEMENT:
             b->numberOfPlaceableArmies += getPlayerIncome(b, b->currentPlayer); /* setupPlacementPhase :642-645 */
-            agent_place(b, b->numberOfPlaceableArmies);
+            sim_placeArmies(b, b->numberOfPlaceableArmies);
             b->currentPhase = ORX_PHASE_ATTACK;
             break;
         case ORX_PHASE_ATTACK:
             setupAttackPhase(b);
-            agent_attackPhase(b);
+            sim_attackPhase(b);
             if (!b->flags) tearDownAttackPhase(b);
             break;
         case ORX_PHASE_FORTIFICATION:
-            b->ct.tv += (uint64_t)b->N; /* setupFortificationPhase sweep :900-906 (dead stores) */
-            tearDownFortificationPhase(b);
+            b->ct.tv += (uint64_t)b->N; /* setupFortificationPhase sweep :900-906 (dead stores for SimRandom) */
+            setupFortificationPhase(b);
+            sim_fortifyPhase(b);
+            if (!b->flags) tearDownFortificationPhase(b);
             step_limit_hit(b);
             break;
         default:
@@ -1272,6 +1549,7 @@ typedef struct OrcCtx {
     OrxMap map; OrxRules rules;
     int32_t *adj_off, *adj, *continent, *bonus, *symbol;
     char *progression;
+    int agents[MAXP], modelling_turn_limit; /* ModellingBoard's constructor arguments */
 } OrcCtx;
 
 OrcCtx *orc_create(const OrxMap *map, const OrxRules *rules)
@@ -1295,6 +1573,19 @@ OrcCtx *orc_create(const OrxMap *map, const OrxRules *rules)
     return c;
 }
 
+/* new ModellingBoard(bs, sas, cm, cid, modellingTurnLimit): see orx_set_sim_agents in include/orx.h */
+int orc_set_sim_agents(OrcCtx *c, const int32_t *agent_ids, int modelling_turn_limit)
+{
+    if (!c) return -1;
+    for (int p = 0; p < MAXP; p++) c->agents[p] = ORX_AGENT_RANDOM;
+    c->modelling_turn_limit = 0;
+    if (!agent_ids || modelling_turn_limit <= 0) return 0;
+    for (int p = 0; p < c->map.n_players; p++) if (agent_ids[p] < 0 || agent_ids[p] >= ORX_AGENT_COUNT) return -1;
+    for (int p = 0; p < c->map.n_players; p++) c->agents[p] = agent_ids[p];
+    c->modelling_turn_limit = modelling_turn_limit;
+    return 0;
+}
+
 void orc_destroy(OrcCtx *c)
 {
     if (!c) return;
@@ -1312,6 +1603,8 @@ static void board_init_static(Board *b, const OrcCtx *c)
     b->progression = parse_progression(c->progression);
     b->maxPlayerTurns = c->rules.max_player_turns > 0 ? c->rules.max_player_turns : (1 << 16);
     b->canRunOutOfCards = b->P * 5 > b->N + 2; /* O/CardManager.java:65 */
+    for (int p = 0; p < MAXP; p++) b->simAgentInitial[p] = c->agents[p];
+    b->modellingTurnLimit = c->modelling_turn_limit;
 }
 
 static void run_one(Board *b, const OrcCtx *c, const uint8_t *leaf, uint64_t seed, uint64_t game,

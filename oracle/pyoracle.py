@@ -46,6 +46,7 @@ def lib():
         L.orc_starting_armies.argtypes = [C.c_int, C.c_int, i32p]; L.orc_starting_armies.restype = C.c_int
         L.orc_create.argtypes = [C.c_void_p, C.c_void_p]; L.orc_create.restype = C.c_void_p
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_sim_agents.argtypes = [C.c_void_p, i32p, C.c_int]; L.orc_set_sim_agents.restype = C.c_int
         L.orc_rollout_batch.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
                                         C.c_void_p, u64p, C.c_int]
         L.orc_rollout_batch.restype = C.c_int
@@ -127,7 +128,7 @@ COUNTER_NAMES = ("tv", "ev", "r_words", "battles", "cdf_steps", "writes", "playe
 class Oracle:
     """setupState + simulate + getters, batched, on the CPU restatement."""
 
-    def __init__(self, risk_map, rules):
+    def __init__(self, risk_map, rules, sim_agents=None, modelling_turn_limit=0):
         from oponn_b200.state import GAME_RESULT_DTYPE, LEAF_RESULT_DTYPE, leaf_layout
         self._gdt, self._ldt = GAME_RESULT_DTYPE, LEAF_RESULT_DTYPE
         self.map, self.rules = risk_map, rules
@@ -136,6 +137,16 @@ class Oracle:
         if not self._h:
             raise ValueError("orc_create rejected the map")
         self.layout = leaf_layout(risk_map.n_territories, risk_map.n_players)
+        if sim_agents is not None:
+            self.set_sim_agents(sim_agents, modelling_turn_limit)
+
+    def set_sim_agents(self, sim_agents, modelling_turn_limit=2):
+        """new ModellingBoard(bs, sas, cm, cid, modellingTurnLimit): agent ids per player (oponn_b200.state.AGENT_*)"""
+        ids = np.asarray(list(sim_agents), dtype=np.int32)
+        if len(ids) != self.map.n_players:
+            raise ValueError("one agent id per player")
+        if lib().orc_set_sim_agents(self._h, _p(ids, C.c_int32), int(modelling_turn_limit)) != 0:
+            raise ValueError("orc_set_sim_agents rejected the agent ids")
 
     def close(self):
         if self._h:

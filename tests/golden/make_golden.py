@@ -11,6 +11,8 @@ Files written:
   classic42_mid_64.leaves  64 packed records, state seeds 1..64 (distinct mid-game positions)
   synth200_mid_s1.leaf     the large-map analogue (BASELINE.json config 4)
   golden_games.npz         per-game result records for those leaves under run seed 20261019
+                           (+ "classic42_mid_s1_modelled": the same leaf with the line-up MODELLED_AGENTS behind
+                           ModellingBoard, turn limit 2 -- written by --modelled without touching the other keys)
 """
 from __future__ import annotations
 
@@ -27,6 +29,7 @@ from oponn_b200.state import PHASE_INITIAL_PLACEMENT, BoardState, Rules  # noqa:
 from oracle.pyoracle import Oracle  # noqa: E402
 
 RUN_SEED = 20261019
+MODELLED_AGENTS = [0, 1, 2, 1, 2, 0]     # SimRandom, SimAngry, SimStinky, ... (oponn_b200.state.AGENT_*)
 
 
 def new_game_leaf(m, state_seed: int) -> np.ndarray:
@@ -105,8 +108,23 @@ def workload(n: int = 16384):
     print("A =", A)
 
 
+def modelled():
+    """per-game records with modelled opponents, added to golden_games.npz."""
+    path = os.path.join(HERE, "golden_games.npz")
+    out = dict(np.load(path))
+    leaf = np.fromfile(os.path.join(HERE, "classic42_mid_s1.leaf"), dtype=np.uint8)
+    o = Oracle(classic42(6), Rules(), sim_agents=MODELLED_AGENTS, modelling_turn_limit=2)
+    _, games = o.rollout_batch(leaf[None, :], 256, RUN_SEED, per_game=True, threads=8)
+    o.close()
+    out["classic42_mid_s1_modelled"] = games
+    np.savez_compressed(path, **out)
+    print("classic42_mid_s1_modelled", games.shape)
+
+
 if __name__ == "__main__":
     if "--workload" in sys.argv:
         workload()
+    elif "--modelled" in sys.argv:
+        modelled()
     else:
         main()

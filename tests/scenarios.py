@@ -5,8 +5,8 @@ restatement of BattleSim.generateAttackOutcomes)."""
 import numpy as np
 
 from battlesim_ref import numpy_outcome_table
-from oponn_b200.state import (ATTACK_EXECUTE, CARD_WILD, PHASE_ATTACK, PHASE_CARDS, PHASE_PLACEMENT, BoardState, RiskMap,
-                              Rules)
+from oponn_b200.state import (AGENT_ANGRY, AGENT_RANDOM, AGENT_STINKY, ATTACK_EXECUTE, CARD_WILD, PHASE_ATTACK, PHASE_CARDS,
+                              PHASE_COUNTRY_SELECTION, PHASE_FORTIFICATION, PHASE_PLACEMENT, BoardState, RiskMap, Rules)
 from scripted import Script, board_hash
 
 
@@ -91,6 +91,97 @@ def scenario_cards_and_income():
 
 
 ALL = [scenario_sweep, scenario_catchup_execute_keeps_owner, scenario_cards_and_income]
+
+
+# ---- modelled opponents: (map, rules, leaf, words, expected, agent ids, modelling turn limit) --------
+
+def scenario_angry_sweep():
+    """SimAngry: placement on the country with most enemy neighbours (SimAngry.java:126-151), attack passes over an
+    ArmiesIterator that holds one element ahead (:157-195), moveArmiesIn by enemy-neighbour counts (:199-213)."""
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[4, 2, 3, 1], currentPlayer=0, currentPhase=PHASE_PLACEMENT,
+                      numberOfPlaceableArmies=3, playerNumberOfCards=[0, 0])
+    assert first_row(4, 3) == (0, 3, True) and first_row(3, 1) == (0, 1, True)
+    s = Script()
+    # placeArmies(3): country 0 has 0 enemy neighbours, country 1 has 1 -> all 3 on country 1: armies [4, 5, 3, 1]
+    # pass 1: iterator holds 0 then 1 (then nothing: 2 and 3 are not ours when 1 is handed out)
+    #   us = 0: no enemy neighbour.  us = 1: weakest enemy neighbour 2 (3 armies), 5 > 3 -> attack till death
+    s.double_k(0)                  # battle 4 v 3 -> first row (0, 3): conquered
+    #   moveArmiesIn(1, 2): enemies of 1 = 0, enemies of 2 = 1 (country 3) -> not more at home -> move all 4
+    #   armies [4, 1, 4, 1], owner [0, 0, 0, 1]
+    # pass 2: holds 0, then 2 (1 has a single army).  us = 2: weakest 3 (1 army), 4 > 1 -> attack
+    s.double_k(0)                  # battle 3 v 1 -> (0, 1): conquered; moveArmiesIn(2, 3): 0 v 0 enemies -> all 3
+    #   armies [4, 1, 1, 3]; player 1 has no country left -> playerOutOnTurn = [-1, 0], stream position pinned here
+    term = len(s.words)
+    # pass 3: nothing to attack, madeAttack stays false
+    exp = dict(pot=[-1, 0], turns=0, flags=0, stream_pos=term, hash=board_hash([0, 0, 0, 0], [4, 1, 1, 3]))
+    return m, r, leaf, s.array(pad=4), exp, [AGENT_ANGRY, AGENT_RANDOM], 2
+
+
+def scenario_angry_stinky_then_random():
+    """SimAngry.fortifyPhase (SimAngry.java:215-279) from a FORTIFICATION leaf, two SimStinky turns (SimStinky.java:66-125),
+    and ModellingBoard's switch to SimRandom at the second round wrap (ModellingBoard.java:29-47)."""
+    m, r = line4(), Rules(use_cards=False, max_player_turns=5)
+    leaf = BoardState(owner=[0, 0, 0, 1], armies=[5, 1, 2, 9], currentPlayer=0, currentPhase=PHASE_FORTIFICATION,
+                      playerNumberOfCards=[0, 0])
+    assert first_row(11, 3) == (0, 3, True) and first_row(16, 9) == (5, 9, True) and first_row(3, 11) == (3, 0, False)
+    s = Script()
+    # catch-up fortifyPhase of player 0 (Angry), moveable = [5, 1, 2, 0]:
+    #   i = 0: its only neighbour 1 has no enemy neighbour, neither has 0 -> random neighbour
+    s.int(1, 0)                    #   -> country 1; fortify min(5, moveable 5, armies - 1 = 4) = 4: armies [1, 5, 2, 9]
+    #   i = 1 (moveable 1): neighbour 2 has 1 enemy neighbour > 0 of its own -> fortify 1: armies [1, 4, 3, 9]
+    #   i = 2 (moveable 2): no better neighbour, has an enemy neighbour itself -> stays
+    # player 1 (Stinky): income max(1 / 3, 3) = 3
+    s.int(4, 0).int(4, 3)          # placeArmies: country 0 is not ours -> redraw; country 3 borders an enemy: armies [1, 4, 3, 12]
+    s.double_k(0)                  # attackPhase(true): us = 3, weak = 2 (3 armies), 12 > 4.5 -> battle 11 v 3 -> (0, 3)
+    #   moveArmiesIn(3, 2): country 3 has no enemy neighbour any more -> 1000000 -> clamped to 11: armies [1, 4, 11, 1]
+    # wrap to player 0: simTurnCount 0 -> 1, no switch yet (0 + 1 != 2)
+    # player 0 (Angry): income 3 + continent 0 (bonus 2) = 5 on country 1 (1 enemy neighbour): armies [1, 9, 11, 1]
+    #   attack: us = 1, weakest 2 (11 armies), 9 > 11 is false.  fortify: 0 -> 1 moves min(1, 1, 0) = 0; nothing else
+    # player 1 (Stinky): income 3 + continent 1 (bonus 3) = 6
+    s.int(4, 2)                    # placeArmies: country 2 borders country 1: armies [1, 9, 17, 1]
+    s.double_k(0)                  # us = 2 (holds 3 next), weak = 1 (9 armies), 17 > 13.5 -> battle 16 v 9 -> (5, 9)
+    #   conquered with 12 left; moveArmiesIn(2, 1): no enemy neighbour of 2 -> all 11: armies [1, 11, 1, 1], owner [0, 1, 1, 1]
+    #   us = 3: no enemy neighbour.  13 armies in total, not > 300: no second pass
+    # wrap to player 0: simTurnCount 1, 1 + 1 == 2 -> everybody is SimRandom from here on; simTurnCount = 2
+    s.int(3, 2).int(1, 0)          # SimRandom.place: income 3, 1 + 2 = 3 armies on candidates[0] = country 0: armies [4, 11, 1, 1]
+    s.int(1, 0).int(1, 0)          # SimRandom.attackPhase: attackers [0], defenders [1]
+    s.double_k(0)                  # battle 3 v 11 -> (3, 0): attackers destroyed: armies [1, 11, 1, 1]
+    # fortification -> player 1, fifth player-turn: step limit
+    exp = dict(pot=[0, 0], turns=2, flags=2, stream_pos=len(s.words), hash=board_hash([0, 1, 1, 1], [1, 11, 1, 1]))
+    return m, r, leaf, s.array(pad=4), exp, [AGENT_ANGRY, AGENT_STINKY], 2
+
+
+def scenario_angry_draft():
+    """SimAngry.pickCountry (SimAngry.java:49-105) with MapHelper's smallest positive empty / open continent
+    (MapHelper.java:132-191), against a SimRandom drafter; first initial placements, then the step limit."""
+    m, r = line4(), Rules(use_cards=False, max_player_turns=2)
+    leaf = BoardState(owner=[-1, -1, -1, -1], armies=[1, 1, 1, 1], currentPlayer=0, currentPhase=PHASE_COUNTRY_SELECTION,
+                      playerNumberOfCards=[0, 0])
+    s = Script()
+    # player 0 (Angry): both continents empty, size 2, positive bonus -> continent 0; no neighbour of ours there ->
+    #   fewest neighbours: country 0 (1 neighbour)
+    s.int(3, 1)                    # player 1 (SimRandom.pickCountry): unowned [1, 2, 3] -> country 2
+    # player 0: no continent is empty any more; smallest open one = continent 0; country 1 neighbours our country 0
+    s.int(1, 0)                    # player 1: unowned [3]
+    # INITIAL_PLACEMENT: 22 starting armies each (N = 4, P = 2), 2 countries taken -> 20 left, 4 per turn
+    #   player 0 (Angry): country 1 has the enemy neighbour -> armies [1, 5, 1, 1]
+    s.int(4, 3).int(1, 0)          #   player 1 (SimRandom.place): 1 + 3 = 4 armies on candidates[0] = country 2
+    exp = dict(pot=[0, 0], turns=0, flags=2, stream_pos=len(s.words), hash=board_hash([0, 0, 1, 1], [1, 5, 5, 1]))
+    return m, r, leaf, s.array(pad=4), exp, [AGENT_ANGRY, AGENT_RANDOM], 2
+
+
+def scenario_stinky_cannot_draft():
+    """SimStinky.pickCountry returns -1 (SimStinky.java:51-54); SimulationBoard.selectCountry prints "Err..." and then
+    indexes countries[-1] (SimulationBoard.java:485-494): the playout dies with an exception -> ORX_FLAG_ERROR."""
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[-1, -1, -1, -1], armies=[1, 1, 1, 1], currentPlayer=0, currentPhase=PHASE_COUNTRY_SELECTION,
+                      playerNumberOfCards=[0, 0])
+    exp = dict(pot=[0, 0], turns=0, flags=1, stream_pos=0, hash=0)
+    return m, r, leaf, Script().array(pad=4), exp, [AGENT_STINKY, AGENT_RANDOM], 2
+
+
+MODELLED = [scenario_angry_sweep, scenario_angry_stinky_then_random, scenario_angry_draft, scenario_stinky_cannot_draft]
 
 
 def check(games_row, exp, n_players):

@@ -135,6 +135,62 @@ def test_hand_derived_scenarios(make):
     scenarios.check(games[0], exp, m.n_players)
 
 
+@pytest.mark.parametrize("make", scenarios.MODELLED, ids=lambda f: f.__name__)
+def test_hand_derived_modelled_opponents(make):
+    """SimAngry / SimStinky behind ModellingBoard, expectations worked out by hand."""
+    from oponn_b200.engine import RolloutEngine
+    m, r, leaf, words, exp, agents, limit = make()
+    with RolloutEngine(m, r, 0, sim_agents=agents, modelling_turn_limit=limit) as e:
+        games = e.rollout_replay(leaf.pack(m)[None, :], words[None, :])
+    scenarios.check(games[0], exp, m.n_players)
+
+
+def test_modelled_opponents_match_oracle(classic, rules, mid_leaf, golden_games):
+    """Every per-game record with modelled line-ups equals the oracle's: mid-game leaf, the phase zoo (pre-game and
+    mid-game), turn limit 2 (the reference's) and "never switch back"; then modelling off again == the plain goldens."""
+    from leafzoo import phase_zoo
+    from oponn_b200.engine import RolloutEngine
+    from oracle.pyoracle import Oracle
+    e, o = RolloutEngine(classic, rules, 0), Oracle(classic, rules)
+    gold = golden_games["classic42_mid_s1_modelled"]
+    e.set_sim_agents([0, 1, 2, 1, 2, 0], 2)
+    _, games = e.rollout_batch(mid_leaf[None, :], len(gold), RUN_SEED, per_game=True)
+    same(games, gold)
+    for agents in ([1] * 6, [2] * 6, [0, 1, 2, 1, 2, 0], [2, 0, 0, 1, 0, 0]):
+        for limit in (2, 1 << 20):
+            e.set_sim_agents(agents, limit); o.set_sim_agents(agents, limit)
+            _, g = e.rollout_batch(mid_leaf[None, :], 192, 77, per_game=True)
+            _, w = o.rollout_batch(mid_leaf[None, :], 192, 77, per_game=True, threads=8)
+            same(g, w)
+            for base in (None, mid_leaf):
+                leaves, _ = phase_zoo(classic, base)
+                _, g = e.rollout_batch(leaves, 3, 13, per_game=True)
+                _, w = o.rollout_batch(leaves, 3, 13, per_game=True, threads=8)
+                same(g, w)
+    e.set_sim_agents(None)
+    _, games = e.rollout_batch(mid_leaf[None, :], 64, RUN_SEED, per_game=True)
+    same(games, golden_games["classic42_mid_s1"][:64])
+    e.close(); o.close()
+
+
+def test_modelled_opponents_large_map(golden_games):
+    """the 8-word board scans (territories > 64) of the modelled policies"""
+    from leafzoo import phase_zoo
+    m, r = synth200(), Rules(max_player_turns=4096)
+    e, o = pair(m, r)
+    leaf = np.fromfile(os.path.join(GOLDEN, "synth200_mid_s1.leaf"), dtype=np.uint8)
+    agents = [1, 2, 0, 1, 2, 1, 2, 0]
+    e.set_sim_agents(agents, 3); o.set_sim_agents(agents, 3)
+    _, g = e.rollout_batch(leaf[None, :], 24, 5, per_game=True)
+    _, w = o.rollout_batch(leaf[None, :], 24, 5, per_game=True, threads=8)
+    same(g, w)
+    leaves, _ = phase_zoo(m, None)
+    _, g = e.rollout_batch(leaves, 2, 5, per_game=True)
+    _, w = o.rollout_batch(leaves, 2, 5, per_game=True, threads=8)
+    same(g, w)
+    e.close(); o.close()
+
+
 def test_goldens(engine, mid_leaf, golden_games):
     gold = golden_games["classic42_mid_s1"]
     agg, games = engine.rollout_batch(mid_leaf[None, :], len(gold), RUN_SEED, per_game=True)

@@ -22,6 +22,16 @@ def test_hand_derived_scenarios(make):
     scenarios.check(games[0], exp, m.n_players)
 
 
+@pytest.mark.parametrize("make", scenarios.MODELLED, ids=lambda f: f.__name__)
+def test_hand_derived_modelled_opponents(make):
+    """SimAngry / SimStinky behind ModellingBoard, worked out by hand from the reference's source."""
+    m, r, leaf, words, exp, agents, limit = make()
+    o = Oracle(m, r, sim_agents=agents, modelling_turn_limit=limit)
+    games = o.rollout_replay(leaf.pack(m)[None, :], words[None, :])
+    o.close()
+    scenarios.check(games[0], exp, m.n_players)
+
+
 def test_golden_regression(oracle, mid_leaf, golden_games):
     """The committed per-game records are what today's oracle produces (guards the checker itself)."""
     gold = golden_games["classic42_mid_s1"]
@@ -31,6 +41,41 @@ def test_golden_regression(oracle, mid_leaf, golden_games):
     gold = golden_games["classic42_mid_64"]
     _, games = oracle.rollout_batch(leaves, 4, RUN_SEED, per_game=True, threads=8)
     assert games.tobytes() == gold.tobytes()
+
+
+def test_golden_regression_modelled_opponents(classic, rules, mid_leaf, golden_games):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = golden_games["classic42_mid_s1_modelled"]
+    o = Oracle(classic, rules, sim_agents=mg.MODELLED_AGENTS, modelling_turn_limit=2)
+    _, games = o.rollout_batch(mid_leaf[None, :], len(gold), RUN_SEED, per_game=True, threads=8)
+    assert games.tobytes() == gold.tobytes()
+    # an all-SimRandom line-up behind ModellingBoard is the plain board (ModellingBoard.java:29-47)
+    o.set_sim_agents([0] * 6, 2)
+    _, games = o.rollout_batch(mid_leaf[None, :], 64, RUN_SEED, per_game=True, threads=8)
+    o.close()
+    assert games.tobytes() == golden_games["classic42_mid_s1"][:64].tobytes()
+
+
+def test_modelled_opponents_play_every_phase_to_the_end(classic, rules, mid_leaf):
+    """SimAngry / SimStinky line-ups from every phase; SimStinky cannot draft (its pickCountry returns -1 and
+    SimulationBoard.selectCountry throws, SimulationBoard.java:485-494) -> those playouts carry FLAG_ERROR."""
+    from leafzoo import phase_zoo
+    from oponn_b200.state import AGENT_ANGRY, AGENT_STINKY
+    for agents in ([AGENT_ANGRY] * 6, [AGENT_STINKY] * 6, [0, 1, 2, 1, 2, 0]):
+        for limit in (2, 1 << 20):
+            o = Oracle(classic, rules, sim_agents=agents, modelling_turn_limit=limit)
+            for base in (None, mid_leaf):
+                leaves, names = phase_zoo(classic, base)
+                _, games = o.rollout_batch(leaves, 4, 11, per_game=True, threads=8)
+                games = games.reshape(len(names), 4)
+                for i, name in enumerate(names):
+                    if name.startswith("country_selection") and AGENT_STINKY in agents:
+                        continue
+                    assert np.all(games[i]["flags"] == 0), (agents, limit, name)
+                    assert np.all((games[i]["player_out_on_turn"][:, :6] == -1).sum(axis=1) == 1), (agents, limit, name)
+            o.close()
 
 
 def test_golden_regression_large_map(golden_games):
