@@ -821,7 +821,7 @@ struct Game {
             if (s.flags) return;
             cc = nth_territory(free_, i);
         }
-        if (cc < 0 || owner(cc) != (int)ORX_OWNER_NONE) { fail(); return; }  // selectCountry (:485-494)
+        if (MODEL && (cc < 0 || owner(cc) != (int)ORX_OWNER_NONE)) { fail(); return; }  // selectCountry (:485-494); a SimRandom pick is always free
         set_owner(cc, cp);
         if (lane == cp) { pc++; ialp--; }
         set_hdr(WH_REM_COUNTRIES, hdr(WH_REM_COUNTRIES) - 1u);
