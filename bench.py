@@ -275,7 +275,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": stride * world,
                     "d2h_bytes_per_step": LEAF_RESULT_DTYPE.itemsize * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "int_issue", "kernel": "orx::rollout_kernel<2,false>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "int_issue", "kernel": "orx::rollout_kernel<2,false,false>", "achieved": achieved, "peak": peak,
                          "unit": "Gop/s", "frac": achieved / peak,
                          "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']} MHz "
                                         f"({peaks['_source']} clock, MEASURED_PEAKS.json)",
