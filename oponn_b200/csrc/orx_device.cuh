@@ -46,9 +46,6 @@ struct DevMap {
     int32_t bonus_off;          // i32 [C]         initialContinentBonuses
     // per-warp dynamic slice (bytes from the slice base)
     int32_t w_rng, w_armies, w_owner, w_alist, w_cards, w_bytes;
-    int32_t w_move;             // moveable armies (i32 [NP]); only laid out while opponent modelling is on
-    int32_t model_limit;        // ModellingBoard.modellingTurnLimit, 0 = modelling off
-    uint32_t agents;            // ORX_AGENT_* of player p in bits 3p..3p+2
     int32_t leaf_stride, off_owner, off_armies, off_ncards, off_cards;
     int32_t start_armies;       // calculateStartingArmies base (SimulationBoard.java:518-533)
     const uint8_t  *blob;       // global copy of the static map image
@@ -57,6 +54,11 @@ struct DevMap {
     const uint32_t *bt_meta;    // [100*100] (row offset << 8) | row count   for (a,d)
     const uint64_t *bt_rows;    // (min(floor(cdf * 2^53), 2^53-1) << 11) | invading << 7 | survivors
     uint64_t single_thr[6][2];  // floor(cdf*2^53) of BattleSim.outcomes rows (O/BattleSim.java:36-44)
+    // opponent modelling (MODEL instantiations; kept at the end so the all-SimRandom kernels see the layout they were tuned on)
+    int32_t w_move;             // per-warp slice: moveable armies (i32 [NP]); only laid out while modelling is on
+    int32_t model_limit;        // ModellingBoard.modellingTurnLimit, 0 = modelling off
+    uint32_t agents;            // ORX_AGENT_* of player p in bits 3p..3p+2
+    int32_t reserved_;
 };
 
 // floor(2^32 / b) + 1 for b < ORX_MAGIC_N: u % b for u < 2^31 in four instructions (next_int)

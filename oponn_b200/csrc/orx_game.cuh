@@ -335,9 +335,23 @@ struct Game {
     // simAgents[currentPlayer].moveArmiesIn + executeInvasion
     __device__ __forceinline__ void invade(int A, int D)
     {
-        int req = MODEL ? sim_move_in(A, D) : random_move_in(A);
-        if (s.flags) return;
-        execute_invasion(A, D, req);
+        if (MODEL) {
+            int req = sim_move_in(A, D);
+            if (s.flags) return;
+            execute_invasion(A, D, req);
+            return;
+        }
+        // all-SimRandom instantiation: SimRandom.moveArmiesIn and executeInvasion fused, as the kernel was tuned
+        int aArm = armies(A);
+        int available = aArm - 1;
+        if (available == 0) { fail(); return; }
+        int mn = available < 3 ? available : 3;
+        int req = mn + (mn == available ? 0 : s.next_int(available - mn));
+        int lo = aArm - 1 < 3 ? aArm - 1 : 3, hi = aArm - 1;
+        int inv = req > lo ? req : lo; if (inv > hi) inv = hi;
+        __syncwarp();
+        if (lane == 0) { sts32(a_arm + 4u * (uint32_t)D, (uint32_t)inv); sts32(a_arm + 4u * (uint32_t)A, (uint32_t)(aArm - inv)); }
+        __syncwarp();
     }
 
     // finishInvasion (:827-841)

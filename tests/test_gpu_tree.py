@@ -59,6 +59,26 @@ def test_batched_agrees_with_one_leaf_at_a_time(engine, classic, mid_leaf):
         assert int(top["type"]) in (MOVE_ATTACK, MOVE_NEXT_PHASE)
 
 
+def test_search_with_modelled_opponents(classic, mid_leaf):
+    """Opponent modelling is a property of the rollout context (orx_set_sim_agents): the same search, with every
+    opponent of player 0 modelled (Oponn.createSimAgents: simAgents[ID] itself stays SimRandom), keeps the bookkeeping
+    identities and evaluates the root differently from the all-SimRandom line-up."""
+    from oponn_b200.engine import RolloutEngine
+    from oponn_b200.state import AGENT_ANGRY, AGENT_RANDOM, AGENT_STINKY
+    bs = attack_leaf(classic, mid_leaf)
+    rate = {}
+    for name, agents in (("random", None), ("modelled", [AGENT_RANDOM, AGENT_ANGRY, AGENT_STINKY, AGENT_ANGRY, AGENT_STINKY, AGENT_ANGRY])):
+        with RolloutEngine(classic, Rules(), 0, sim_agents=agents, modelling_turn_limit=2) as e:
+            tree = SearchTree(classic, Rules(), TreeOptions(agent_id=0, playouts_per_leaf=8, leaves_in_flight=256, seed=3), e)
+            ch, st = tree.search(bs, 1000)
+            tree.close()
+        assert int(ch["visits"].sum()) == 8000 and np.all(ch["wins"][:, :6].sum(axis=1) == ch["visits"])
+        rate[name] = ch["wins"][:, :6].sum(axis=0) / 8000.0
+    # two methodical rounds of five opponents change who tends to win from this position (8000 playouts each: the
+    # binomial sigma of a rate is below 0.006)
+    assert np.abs(rate["random"] - rate["modelled"]).max() > 0.03, rate
+
+
 def test_forced_move_stops_early(engine, classic, mid_leaf):
     """one legal move: the loop ends after the first expansion (MCTSTree.java:179)"""
     tree = SearchTree(classic, Rules(), TreeOptions(playouts_per_leaf=2, leaves_in_flight=64), engine)
