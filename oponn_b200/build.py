@@ -46,6 +46,8 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
     if not (force or is_stale()):
         return LIB
     flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    if os.environ.get("ORX_PAD"):                   # tuning knob: code alignment of the rollout kernels
+        flags = flags + [f"-DORX_PAD={int(os.environ['ORX_PAD'])}"]
     if os.environ.get("ORX_NVVM_MIN_BLOCKS"):      # tuning knob: the loose bound the front end sees
         flags = flags + [f"-DORX_MIN_BLOCKS={int(os.environ['ORX_NVVM_MIN_BLOCKS'])}"]
     if not uniform:

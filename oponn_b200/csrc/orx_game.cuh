@@ -1120,6 +1120,10 @@ template <int NWT, bool REPLAY, bool MODEL>
 __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ RolloutArgs ar)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+#ifdef ORX_PAD   // tuning knob: shifts the code that follows by ORX_PAD instructions (fetch alignment of the hot loops)
+#pragma unroll
+    for (int i = 0; i < ORX_PAD; i++) asm volatile("bar.warp.sync 0xffffffff;");
+#endif
     // stage the static map image
     {
         const uint4 *src = (const uint4 *)dm.blob; uint4 *dst = (uint4 *)smem;
