@@ -16,7 +16,7 @@ import com.mld46.oponn.CardManager;
  *     if (simOngoing) { expansion(path); gpu.simulate(explorationBoard.getBoardState()); }
  *     backpropagation(path):  for j < cores: playerOutOnTurn = gpu.playerOutOnTurn(j); finalTurn = gpu.simTurnCount(j);
  *
- * NOT COMPILED in the build image (no JDK): reference-side glue for a maintainer.  Orx is in INTEGRATION.md.
+ * NOT COMPILED in the build image (no JDK): reference-side glue for a maintainer.  Orx.java is next to this file.
  */
 public final class GpuSimulation implements AutoCloseable {
     private static final int GAME_RESULT_BYTES = 48;   // OrxGameResult: int32 playerOutOnTurn[8], simTurnCount, flags, streamPos, boardHash
