@@ -125,6 +125,30 @@ def test_card_cash_values():
                 assert e.card_cash_value(pos) == pyoracle.card_cash_value(prog, pos), (prog, pos)
 
 
+# ---- the ABI from plain C --------------------------------------------------------------------------------------
+def test_c_program_gets_the_same_numbers(tmp_path):
+    """examples/orx_demo.c (gcc, no Python in the process) against the ctypes binding on the same map and leaf"""
+    import subprocess
+    from test_abi_and_host import build_c_demo
+    from oponn_b200.engine import RolloutEngine
+    from oponn_b200.state import PHASE_CARDS, BoardState, RiskMap
+    exe = build_c_demo(tmp_path)
+    r = subprocess.run([exe, "-", "4096", "77"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    words = r.stdout.split()
+    wins_c = [int(x) for x in words[words.index("wins") + 1:words.index("wins") + 7]]
+    n = 42
+    m = RiskMap(name="ring42", n_players=6, adjacency=[[(t - 1) % n, (t + 1) % n] for t in range(n)],
+                continent=[t // 7 for t in range(n)], continent_bonus=[5, 2, 5, 3, 7, 2])
+    bs = BoardState(owner=[t % 6 for t in range(n)], armies=[3] * n, currentPlayer=0, currentPhase=PHASE_CARDS, turnCount=1,
+                    playerNumberOfCards=[0] * 6, hand=[], deck=list(range(n)) + [0xFF, 0xFF], cardProgressionPos=1,
+                    attackUntilDead=True)
+    with RolloutEngine(m, Rules(), 0) as e:
+        agg, _ = e.rollout_batch(bs.pack(m)[None, :], 4096, 77, per_game=False)
+    assert [int(x) for x in agg["wins"][0][:6]] == wins_c and int(agg["n"][0]) == 4096
+    assert f"playouts 4096 flagged {int(agg['flagged'][0])}" in r.stdout
+
+
 # ---- whole games ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("make", scenarios.ALL, ids=lambda f: f.__name__)
 def test_hand_derived_scenarios(make):
