@@ -428,6 +428,30 @@ def test_random_maps_and_leaves_fuzz():
             e.close(); o.close()
 
 
+def test_random_maps_and_leaves_fuzz_modelled_opponents():
+    """the same fuzz with random SimRandom / SimAngry / SimStinky line-ups and modelling turn limits (f4)"""
+    from leafzoo import random_leaves, random_map
+    rng = np.random.default_rng(20261021)
+    for k in range(10):
+        n = int(rng.choice([5, 12, 32, 33, 42, 64, 65, 120]))
+        p = int(rng.integers(2, 9))
+        m = random_map(rng, n, p, int(rng.integers(1, 9)))
+        r = Rules(use_cards=bool(rng.random() < 0.8), transfer_cards=bool(rng.integers(2)), continent_increase=int(rng.choice([0, 0, 5])),
+                  max_player_turns=int(rng.choice([200, 1000])))
+        leaves = random_leaves(m, rng, 120 if n <= 64 else 40)
+        agents = [int(x) for x in rng.integers(0, 3, size=p)]
+        limit = int(rng.choice([1, 2, 3, 1 << 20]))
+        e, o = pair(m, r)
+        try:
+            e.set_sim_agents(agents, limit); o.set_sim_agents(agents, limit)
+            agg, games = e.rollout_batch(leaves, 2, 4321 + k, per_game=True)
+            oagg, ogames = o.rollout_batch(leaves, 2, 4321 + k, per_game=True, threads=THREADS)
+            same(games, ogames)
+            assert agg.tobytes() == oagg.tobytes()
+        finally:
+            e.close(); o.close()
+
+
 def test_win_rates_under_normal_seeding(engine, oracle, mid_leaf):
     """North-star correctness part 2: with ordinary (different) seeds the engine's root win-rate estimates agree with
     the CPU simulator's within a stated confidence interval: per player, |p_gpu - p_cpu| < 4.5 sigma of the difference
