@@ -452,6 +452,49 @@ def test_random_maps_and_leaves_fuzz_modelled_opponents():
             e.close(); o.close()
 
 
+def test_empty_batches_and_the_largest_map():
+    """edge sizes: empty batches return without work; the largest map the ABI accepts (252 territories, 8 players,
+    32 continents, one hub with the maximum 32 neighbours, directed and duplicate-free) against the oracle, with and
+    without modelled opponents; armies at the record's upper bound"""
+    from leafzoo import random_leaves
+    from oponn_b200.state import MAX_CONTINENTS, MAX_DEGREE, MAX_PLAYERS, MAX_TERRITORIES, RiskMap
+    n = MAX_TERRITORIES
+    rng = np.random.default_rng(99)
+    adjacency = [[(t - 1) % n, (t + 1) % n] for t in range(n)]               # a ring ...
+    hub = 17
+    spokes = [int(x) for x in rng.choice([t for t in range(n) if abs(t - hub) > 1], size=MAX_DEGREE - 2, replace=False)]
+    adjacency[hub] += spokes                                                  # ... with one hub of degree 32
+    for t in spokes:
+        adjacency[t].append(hub)
+    m = RiskMap(name="max252", n_players=MAX_PLAYERS, adjacency=adjacency, continent=[t % MAX_CONTINENTS for t in range(n)],
+                continent_bonus=[(c % 5) + 1 for c in range(MAX_CONTINENTS)])
+    r = Rules(max_player_turns=600)
+    e, o = pair(m, r)
+    try:
+        leaves = random_leaves(m, rng, 24)
+        agg, games = e.rollout_batch(leaves[:0], 4, 1, per_game=True)
+        assert len(agg) == 0 and len(games) == 0
+        agg, games = e.rollout_batch(leaves, 0, 1, per_game=True)
+        assert len(games) == 0 and int(agg["n"].sum()) == 0
+        agg, games = e.rollout_batch(leaves, 2, 31, per_game=True)
+        oagg, ogames = o.rollout_batch(leaves, 2, 31, per_game=True, threads=THREADS)
+        same(games, ogames)
+        big = leaves.copy()
+        L = e.layout
+        arm = big[:, L.off_armies:L.off_armies + 4 * n].view("<i4")
+        arm[:, ::7] = 1 << 20                                                 # ORX_MAX_ARMIES on every seventh territory
+        agg, games = e.rollout_batch(big, 1, 32, per_game=True)
+        oagg, ogames = o.rollout_batch(big, 1, 32, per_game=True, threads=THREADS)
+        same(games, ogames)
+        agents = [1, 2, 0, 1, 2, 0, 1, 2]
+        e.set_sim_agents(agents, 2); o.set_sim_agents(agents, 2)
+        agg, games = e.rollout_batch(leaves, 2, 33, per_game=True)
+        oagg, ogames = o.rollout_batch(leaves, 2, 33, per_game=True, threads=THREADS)
+        same(games, ogames)
+    finally:
+        e.close(); o.close()
+
+
 def test_win_rates_under_normal_seeding(engine, oracle, mid_leaf):
     """North-star correctness part 2: with ordinary (different) seeds the engine's root win-rate estimates agree with
     the CPU simulator's within a stated confidence interval: per player, |p_gpu - p_cpu| < 4.5 sigma of the difference
