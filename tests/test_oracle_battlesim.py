@@ -105,3 +105,25 @@ def test_card_values_and_starting_armies():
     assert pyoracle.card_cash_value("5, 10, 15... ^10%", 8) == int(40 * 1.1 ** 2)
     # calculateStartingArmies (SimulationBoard.java:518-533), P=6, N=42
     assert pyoracle.starting_armies(42, 6) == [20, 20, 22, 23, 24, 25]
+
+
+def test_table_key_and_dense_row_offsets():
+    """BattleSim keys its HashMap of tables by szudzikMapping(a, d) (O/BattleSim.java:288-291).  The mapping is Szudzik's
+    pairing, injective on the naturals, so a table is identified by (a, d) alone -- which is what lets the engine
+    replace the map by a dense array.  The engine lays table (a, d) out with capacity a + d at the closed-form row
+    offset used by table_battle (csrc/orx_device.cuh); check the closed form against the running sum the table
+    builder uses (csrc/orx_api.cu), that blocks do not overlap, and that a + d bounds the row count."""
+    szudzik = lambda a, b: a * a + a + b if a >= b else a + b * b
+    keys = {szudzik(a, d) for a in range(0, 201) for d in range(0, 201)}
+    assert len(keys) == 201 * 201
+    off, seen_end = 0, 0
+    for a in range(1, 101):
+        for d in range(1, 101):
+            closed = 50 * a * (a - 1) + 5050 * (a - 1) + a * (d - 1) + (d * (d - 1)) // 2
+            assert closed == off and closed >= seen_end
+            seen_end = closed + a + d
+            off += a + d
+    assert off == 2 * 100 * (100 * 101 // 2)            # kTableRows
+    for a, d in ((1, 1), (2, 1), (3, 2), (7, 5), (20, 20), (3, 40)):
+        prob, al, dl, inv = pyoracle.get_attack_outcomes(a, d)
+        assert len(prob) <= a + d                        # outcomes: (0, 1..d) and (1..a, 0)
