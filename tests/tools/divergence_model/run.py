@@ -9,9 +9,10 @@ visit of every playout (N new game, P turn preamble, S attack selection, R singl
 G gaussian battle); two small C programs replay those per-game state sequences through a warp of 32 lanes
 (lane_sim.c) or G groups (group_sim.c) under several scheduling policies and add up per-state instruction costs.
 
-    python scripts/divergence_model/run.py [playouts=512]
+    python tests/tools/divergence_model/run.py [playouts=512]
 
-Nothing here is used by the product, the tests or the bench.
+Analysis tooling that drives the oracle, hence kept under tests/ (the oracle is test infrastructure); nothing here is
+used by the product, collected by pytest or run by the bench.
 """
 import ctypes as C
 import os
@@ -21,7 +22,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+ROOT = os.path.abspath(os.path.join(HERE, "..", "..", ".."))
 OUT = os.path.join(ROOT, "gpurun_out", "divergence_model")
 sys.path.insert(0, ROOT)
 
