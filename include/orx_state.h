@@ -160,16 +160,46 @@ typedef struct OrxLeafHeader {
     uint8_t n_hand;            /* |CardManager.inHand|: the real hand, handed to
                                   whoever is current_player (SimulationBoard.java:215-218) */
     uint8_t n_deck;            /* |CardManager.notInHand|: the unseen deck, in list order */
-    uint8_t reserved[10];      /* [0]: tree-only, Attack.attackUntilDead of a pending (EXECUTE) attack as the
-                                  exploration board holds it (orx_tree.h); rollouts ignore all ten bytes */
+    uint8_t tree_attack_until_dead; /* tree-only: Attack.attackUntilDead of a pending (EXECUTE) attack as the
+                                  exploration board holds it (orx_tree.h); rollouts ignore it            */
+    uint8_t deal_mode;         /* ORX_DEAL_*: where CardManager.simDeal's nextInt comes from (below)    */
+    int32_t deal_seed;         /* what simDeck.hashCode() returned in CardManager.simReset
+                                  (CardManager.java:245); only read when deal_mode == ORX_DEAL_LEAF_LCG  */
+    uint8_t reserved[4];
 } OrxLeafHeader;
+
+/* Hidden-hand determinisation (CardManager.java:240-263).  CardManager.simReset runs on EVERY
+ * setupState and re-creates its generator as `new Random(simDeck.hashCode())`; every simDeal of the playout that
+ * follows (the hidden hands dealt in setupCardState, SimulationBoard.java:205-227, and the card dealt after an attack
+ * phase with a conquest, :884-896) draws `random.nextInt(deck.size())` from THAT java.util.Random -- so all playouts
+ * of one leaf see the same hidden hands and the same deal sequence.  Card.hashCode() belongs to the un-vendored SDK
+ * (identity hash unless overridden), so the value cannot be recomputed here: the host injects what the call returned.
+ *   ORX_DEAL_LEAF_LCG (default, the reference's behaviour): deals come from a java.util.Random LCG (48-bit state,
+ *       scrambled seed (deal_seed ^ 0x5DEECE66D) & (2^48-1), nextInt as documented) private to the playout; they do
+ *       NOT consume words of the injected stream.
+ *   ORX_DEAL_GAME_STREAM (option): deals draw nextInt from the playout's own word stream, i.e. hidden hands are
+ *       re-sampled per playout (the round-1 behaviour; a Java harness must then hand CardManager.random the word
+ *       source instead of letting simReset re-seed it).
+ * Hosts without a JVM (oponn_b200.state, orx_tree) use orx_deck_hash() below as a stand-in for hashCode(): what
+ * matters is "same deck, same hidden hands". */
+enum { ORX_DEAL_LEAF_LCG = 0, ORX_DEAL_GAME_STREAM = 1 };
+
+static inline ORX_HD int32_t orx_deck_hash(const uint8_t *deck, int n)
+{
+    uint64_t h = 1469598103934665603ull;             /* FNV-1a over the deck's card codes, folded to 32 bits */
+    for (int i = 0; i < n; i++) { h ^= deck[i]; h *= 1099511628211ull; }
+    return (int32_t)(uint32_t)(h ^ (h >> 32));
+}
 
 /* Leaf validity (engine contract; the reference would throw, loop or index out of bounds on
  * most of these -- SimulationBoard.java:357,430; here the playout is flagged ORX_FLAG_ERROR):
  *   0 <= current_player < P;  phase in COUNTRY_SELECTION..FORTIFICATION;  attack_state in START..PLACE;
  *   -1 <= attacking_cc, defending_cc < N;  -1 <= defending_player < P;  card_pos >= 0;
  *   |placeable| <= ORX_MAX_ARMIES;  n_hand + n_deck <= N + 2;  every card is a territory code or ORX_CARD_WILD;
- *   every owner is < P (or ORX_OWNER_NONE while phase == COUNTRY_SELECTION);  1 <= armies[t] <= ORX_MAX_ARMIES.
+ *   every owner is < P (or ORX_OWNER_NONE while phase == COUNTRY_SELECTION);  1 <= armies[t] <= ORX_MAX_ARMIES,
+ *   except that armies[defending_cc] may be 0 in an ATTACK / INVADE leaf (ExplorationBoard.getBoardState after an
+ *   invading AttackOutcome: finishAttack left it at 0 and executeInvasion overwrites it, SimulationBoard.java:814-825);
+ *   deal_mode is an ORX_DEAL_* value.
  * A flagged playout (ORX_FLAG_ERROR or ORX_FLAG_STREAM_END) reports only its first fault -- exactly one of the
  * two bits -- and every other field of its OrxGameResult is zero. */
 typedef struct OrxLeafLayout {
@@ -236,10 +266,11 @@ typedef struct OrxLeafResult {
  * A Java harness reproduces a playout by giving BattleSim.random, SimRandom.random,
  * CardManager.random and Card.getRandomSet the same word source.
  *
- * Counter mode: w_i = Philox4x32-10( ctr = {32*(i/128) + i%32, 0, game_lo, game_hi},
- *                                    key = {seed_lo, seed_hi} )[ (i/32) % 4 ]
- * i.e. words come in blocks of 128: lane l of a warp evaluates counter 32*block+l once
- * and the four outputs of all 32 lanes are consumed component-major.
+ * Counter mode: w_i = Philox4x32-10( ctr = {i / 4, 0, game_lo, game_hi}, key = {seed_lo, seed_hi} )[ i % 4 ]
+ * i.e. the four outputs of counter j are words 4j .. 4j+3: a warp that evaluates 32 consecutive counters holds 128
+ * consecutive words with lane l owning words 4l .. 4l+3 (two nextDouble()s), and a single thread can walk the same
+ * stream four words at a time.  (Round 1 consumed the block component-major; changed in round 2, oracle and goldens
+ * in lock-step.)
  * Replay mode: w_i = words[i] from a caller-supplied array.
  */
 

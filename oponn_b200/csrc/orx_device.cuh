@@ -65,8 +65,9 @@ struct DevMap {
 __constant__ uint32_t c_magic[ORX_MAGIC_N];
 
 // per-warp header words (uint32 indices into the first 32 bytes of the slice)
-enum { WH_GAUSS_LO = 0, WH_GAUSS_HI = 1, WH_HAVE_GAUSS = 2, WH_G0 = 3, WH_G1 = 4, WH_SIM_START = 5, WH_REM_COUNTRIES = 6 };
-#define ORX_WARP_HDR_BYTES 32
+enum { WH_GAUSS_LO = 0, WH_GAUSS_HI = 1, WH_HAVE_GAUSS = 2, WH_G0 = 3, WH_G1 = 4, WH_SIM_START = 5, WH_REM_COUNTRIES = 6,
+       WH_DEAL_LO = 7, WH_DEAL_HI = 8, WH_DEAL_MODE = 9 };   // CardManager.random (48-bit java.util.Random state) + ORX_DEAL_*
+#define ORX_WARP_HDR_BYTES 48
 
 __device__ __forceinline__ int lane_id() { int l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -104,15 +105,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// all 32 lanes evaluate one Philox counter each: 128 words, component-major (orx_state.h)
+// all 32 lanes evaluate one Philox counter each: 128 consecutive words, lane l owning words 4l .. 4l+3 (orx_state.h)
 __device__ __noinline__ void philox_refill(saddr buf, uint32_t blk, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1)
 {
     uint32_t o[4];
     int l = lane_id();
     philox4x32_10(blk * 32u + (uint32_t)l, 0u, g0, g1, k0, k1, o);
     __syncwarp();
-    saddr a = buf + 4u * (uint32_t)l;
-    sts32(a, o[0]); sts32(a + 128u, o[1]); sts32(a + 256u, o[2]); sts32(a + 384u, o[3]);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(buf + 16u * (uint32_t)l), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
     __syncwarp();
 }
 
@@ -197,7 +197,11 @@ struct Stream {
     __device__ __forceinline__ double next_double() { return (double)(long long)next_k53() * 0x1.0p-53; }
 };
 
-// StrictMath.log == fdlibm __ieee754_log, restated with explicitly unfused IEEE operations.
+// StrictMath.log == fdlibm __ieee754_log (e_log.c), restated with explicitly unfused IEEE operations.  The algorithm
+// and its constants are fdlibm's:
+//   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+//   Developed at SunPro, a Sun Microsystems, Inc. business.  Permission to use, copy, modify, and distribute this
+//   software is freely granted, provided that this notice is preserved.
 __device__ __noinline__ double fdlibm_log(double x)
 {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,

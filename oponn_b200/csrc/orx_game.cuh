@@ -175,7 +175,28 @@ struct Game {
     {
         int n = list_len(dm.P);
         if (n == 0) { if (!dm.can_run_out) fail(); return -1; }
-        return list_remove_at(dm.P, s.next_int(n));
+        return list_remove_at(dm.P, hdr(WH_DEAL_MODE) == (uint32_t)ORX_DEAL_GAME_STREAM ? s.next_int(n) : deal_next_int(n));
+    }
+    // CardManager.random = new Random(simDeck.hashCode()) (CardManager.java:245): java.util.Random's own LCG, private to
+    // the playout, state in the warp header (one deal per player-turn at most)
+    __device__ __forceinline__ int deal_next31()
+    {
+        uint64_t st = ((uint64_t)hdr(WH_DEAL_HI) << 32) | (uint64_t)hdr(WH_DEAL_LO);
+        st = (st * 0x5DEECE66Dull + 0xBull) & ((1ull << 48) - 1ull);
+        __syncwarp();
+        if (lane == 0) { sts32(a_hdr + 4u * WH_DEAL_LO, (uint32_t)st); sts32(a_hdr + 4u * WH_DEAL_HI, (uint32_t)(st >> 32)); }
+        __syncwarp();
+        return (int)(st >> 17);
+    }
+    __device__ __forceinline__ int deal_next_int(int bound)   // bound > 0
+    {
+        int r = deal_next31();
+        const int m = bound - 1;
+        if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+        for (int u = r;; u = deal_next31()) {
+            r = u % bound;
+            if ((int)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
+        }
     }
 
     // SimulationBoard.cashCards (SimulationBoard.java:577-618) for hand positions i<j<k
@@ -871,14 +892,18 @@ struct Game {
         int h_cp = (int)(int8_t)((h3 >> 16) & 0xFFu), h_phase = (int)(int8_t)(h3 >> 24);
         int h_astate = (int)(int8_t)(h4 & 0xFFu), h_inv = (int)(int8_t)((h4 >> 8) & 0xFFu);
         int h_dp = (int)(int8_t)((h4 >> 16) & 0xFFu), h_aud = (int)(int8_t)(h4 >> 24);
-        int n_hand = (int)(h5 & 0xFFu), n_deck = (int)((h5 >> 8) & 0xFFu);
+        int n_hand = (int)(h5 & 0xFFu), n_deck = (int)((h5 >> 8) & 0xFFu), h_deal_mode = (int)(h5 >> 24);
+        int h_deal_seed = (int)__ldg(hw + 6);
         const int N = dm.N, P = dm.P;
 
         // engine-level record validation (orx_state.h "Leaf validity"): the same rules as the oracle
         bool bad = h_cp < 0 || h_cp >= P || h_phase < 0 || h_phase > ORX_PHASE_FORTIFICATION ||
                    h_astate < 0 || h_astate > ORX_ATTACK_PLACE || h_acc < -1 || h_acc >= N || h_dcc < -1 || h_dcc >= N ||
                    h_dp < -1 || h_dp >= P || h_cardpos < 0 || n_hand + n_deck > N + 2 ||
-                   h_placeable < -ORX_MAX_ARMIES || h_placeable > ORX_MAX_ARMIES;
+                   h_placeable < -ORX_MAX_ARMIES || h_placeable > ORX_MAX_ARMIES ||
+                   (h_deal_mode != (int)ORX_DEAL_LEAF_LCG && h_deal_mode != (int)ORX_DEAL_GAME_STREAM);
+        // an INVADE leaf may carry the conquered country at 0 armies (executeInvasion overwrites it)
+        const int zero_ok = (h_phase == ORX_PHASE_ATTACK && h_astate == ORX_ATTACK_INVADE) ? h_dcc : -1;
 
         // setupCountries (:192-203)
         __syncwarp();
@@ -891,7 +916,7 @@ struct Game {
                 o = __ldg(leaf + dm.off_owner + t);
                 a = __ldg((const int32_t *)(leaf + dm.off_armies) + t);
                 if (!(o < P || (o == (int)ORX_OWNER_NONE && h_phase == ORX_PHASE_COUNTRY_SELECTION))) badt = true;
-                if (a < 1 || a > ORX_MAX_ARMIES) badt = true;
+                if (a < (t == zero_ok ? 0 : 1) || a > ORX_MAX_ARMIES) badt = true;
             }
             sts8(a_own + (uint32_t)t, (uint32_t)o); sts32(a_arm + 4u * (uint32_t)t, (uint32_t)a);
         }
@@ -927,7 +952,12 @@ struct Game {
         termSet = false; termPos = 0;
         pot = 0; ialp = 0;
         ncard = lane == cp ? n_hand : (lane == P ? n_deck : 0);
-        if (lane == 0) { sts32(a_hdr + 4u * WH_SIM_START, (uint32_t)turn_count); sts32(a_hdr + 4u * WH_REM_COUNTRIES, 0u); }
+        if (lane == 0) {
+            sts32(a_hdr + 4u * WH_SIM_START, (uint32_t)turn_count); sts32(a_hdr + 4u * WH_REM_COUNTRIES, 0u);
+            const uint64_t st = ((uint64_t)(long long)h_deal_seed ^ 0x5DEECE66Dull) & ((1ull << 48) - 1ull);   // Random(long seed)
+            sts32(a_hdr + 4u * WH_DEAL_LO, (uint32_t)st); sts32(a_hdr + 4u * WH_DEAL_HI, (uint32_t)(st >> 32));
+            sts32(a_hdr + 4u * WH_DEAL_MODE, (uint32_t)h_deal_mode);
+        }
         __syncwarp();
 
         // setupCardState (:205-227): hidden hands are dealt at random, in player order

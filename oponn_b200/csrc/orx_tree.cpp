@@ -242,9 +242,8 @@ struct Board {
         realDeck.assign(cards + h->n_hand, cards + h->n_hand + h->n_deck);
         realCardPos = h->card_pos;
         simDeck = realDeck; simCardPos = realCardPos;
-        uint64_t hsh = 1469598103934665603ULL;
-        for (uint8_t c : simDeck) { hsh ^= c; hsh *= 1099511628211ULL; }
-        rnd.set_seed(hsh);
+        // random = new Random(simDeck.hashCode()): the record's deal_seed, as the rollout engine uses it (orx_state.h)
+        rnd.set_seed((uint64_t)(int64_t)h->deal_seed);
         for (int p = 0; p < P; p++) {
             playerCards[p].clear();
             if (p == currentPlayer) playerCards[p] = realHand;
@@ -288,7 +287,7 @@ struct Board {
             } else if (attackState == ORX_ATTACK_CASH || attackState == ORX_ATTACK_PLACE) placeable = h->placeable;
             initiatedWithInvasion = attackState == ORX_ATTACK_INVADE;
             minPlacementCC = minAttackSourceCC = minAttackDestinationCC = 0;
-            attackUntilDead = h->reserved[0] != 0;   // the exploration board's own flag (set by the Attack move), tree-only
+            attackUntilDead = h->tree_attack_until_dead != 0;   // the exploration board's own flag (set by the Attack move), tree-only
             break;
         default: break;
         }
@@ -665,7 +664,9 @@ struct Board {
         h->current_player = (int8_t)currentPlayer; h->phase = (int8_t)phase; h->attack_state = (int8_t)attackState;
         h->has_invaded = hasInvaded; h->defending_player = (int8_t)defendingPlayer;
         h->attack_until_dead = 1;  // the simulation boards' sticky bit in steady state
-        h->reserved[0] = attackUntilDead ? 1 : 0;   // tree-only: Attack.attackUntilDead of the pending attack
+        h->tree_attack_until_dead = attackUntilDead ? 1 : 0;   // tree-only: Attack.attackUntilDead of the pending attack
+        h->deal_mode = ORX_DEAL_LEAF_LCG;
+        h->deal_seed = orx_deck_hash(realDeck.data(), (int)realDeck.size());   // stand-in for simDeck.hashCode()
         h->n_hand = (uint8_t)realHand.size(); h->n_deck = (uint8_t)realDeck.size();
         uint8_t *ow = leaf + L.off_owner; int32_t *ar = (int32_t *)(leaf + L.off_armies); uint8_t *nc = leaf + L.off_ncards; uint8_t *cards = leaf + L.off_cards;
         for (int t = 0; t < S.N; t++) { ow[t] = owner[t] < 0 ? (uint8_t)ORX_OWNER_NONE : (uint8_t)owner[t]; ar[t] = armies[t] < 1 ? 1 : armies[t]; }
@@ -785,6 +786,7 @@ extern "C" int orx_new_game(const OrxMap *map, uint64_t seed, void *leaf_out)
     h->n_hand = 0; h->n_deck = (uint8_t)(N + 2);
     for (int i = 0; i < N; i++) cards[i] = (uint8_t)i;                      // CardManager's notInHand: every card, then two wildcards
     cards[N] = ORX_CARD_WILD; cards[N + 1] = ORX_CARD_WILD;
+    h->deal_mode = ORX_DEAL_LEAF_LCG; h->deal_seed = orx_deck_hash(cards, N + 2);
     return ORX_OK;
 }
 

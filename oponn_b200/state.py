@@ -38,6 +38,20 @@ def agent_from_name(name: str) -> int:
 
 HEADER_BYTES = 32
 
+# OrxLeafHeader.deal_mode (orx_state.h): where CardManager.simDeal's nextInt comes from
+DEAL_LEAF_LCG, DEAL_GAME_STREAM = 0, 1
+
+
+def deck_hash(deck: Sequence[int]) -> int:
+    """``orx_deck_hash``: the stand-in for ``simDeck.hashCode()`` (CardManager.java:245) used by hosts without a JVM:
+    FNV-1a over the deck's card codes folded to a signed 32-bit value."""
+    h = 1469598103934665603
+    for c in deck:
+        h = ((h ^ (int(c) & 0xFF)) * 1099511628211) & ((1 << 64) - 1)
+    v = (h ^ (h >> 32)) & 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
 
 class OrxMapC(C.Structure):
     _fields_ = [("n_territories", C.c_int32), ("n_continents", C.c_int32), ("n_players", C.c_int32),
@@ -167,6 +181,11 @@ class BoardState:
     cardProgressionPos: int = 1
     hand: Sequence[int] = ()            # CardManager.inHand (codes, CARD_WILD for the wildcard)
     deck: Optional[Sequence[int]] = None  # CardManager.notInHand in list order; None = all other cards
+    dealSeed: Optional[int] = None      # what simDeck.hashCode() returned (CardManager.java:245); None = deck_hash(deck)
+    dealFromStream: bool = False        # True = ORX_DEAL_GAME_STREAM: deals draw from the playout's word stream (orx_state.h)
+
+    def deal_seed(self, deck: Sequence[int]) -> int:
+        return deck_hash(deck) if self.dealSeed is None else int(self.dealSeed)
 
     def pack(self, m: RiskMap) -> np.ndarray:
         n, p = m.n_territories, m.n_players
@@ -188,7 +207,8 @@ class BoardState:
                                           ("defending_cc", "<i2"), ("card_pos", "<i2"), ("current_player", "i1"),
                                           ("phase", "i1"), ("attack_state", "i1"), ("has_invaded", "i1"),
                                           ("defending_player", "i1"), ("attack_until_dead", "i1"),
-                                          ("n_hand", "u1"), ("n_deck", "u1"), ("reserved", "u1", (10,))]))
+                                          ("n_hand", "u1"), ("n_deck", "u1"), ("tree_attack_until_dead", "u1"),
+                                          ("deal_mode", "u1"), ("deal_seed", "<i4"), ("reserved", "u1", (4,))]))
         assert hdr.dtype.itemsize == HEADER_BYTES
         hdr["turn_count"] = self.turnCount
         hdr["placeable"] = self.numberOfPlaceableArmies
@@ -203,6 +223,8 @@ class BoardState:
         hdr["attack_until_dead"] = int(self.attackUntilDead)
         hdr["n_hand"] = len(hand)
         hdr["n_deck"] = len(deck)
+        hdr["deal_mode"] = DEAL_GAME_STREAM if self.dealFromStream else DEAL_LEAF_LCG
+        hdr["deal_seed"] = self.deal_seed(deck)
         buf[:HEADER_BYTES] = hdr.view(np.uint8)
         own = np.array([OWNER_NONE if o < 0 else o for o in self.owner], dtype=np.uint8)
         buf[L.off_owner:L.off_owner + n] = own
@@ -231,7 +253,8 @@ class BoardState:
                           playerNumberOfCards=[int(x) for x in b[L.off_ncards:L.off_ncards + p]],
                           numberOfPlaceableArmies=i4(4), hasInvadedACountry=bool(i1(17)), attackState=i1(16),
                           attackingCC=i2(8), defendingCC=i2(10), defendingPlayer=i1(18), attackUntilDead=bool(i1(19)),
-                          cardProgressionPos=i2(12), hand=cards[:n_hand], deck=cards[n_hand:])
+                          cardProgressionPos=i2(12), hand=cards[:n_hand], deck=cards[n_hand:],
+                          dealSeed=i4(24), dealFromStream=int(b[23]) == DEAL_GAME_STREAM)
 
 
 def pack_leaves(m: RiskMap, states: Sequence[BoardState]) -> np.ndarray:

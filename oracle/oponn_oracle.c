@@ -93,11 +93,11 @@ static uint32_t stream_word(Stream *s)
     int64_t blk = i >> 7;
     if (blk != s->buf_block) {
         uint32_t key[2] = { (uint32_t)s->seed, (uint32_t)(s->seed >> 32) };
-        for (uint32_t l = 0; l < 32; l++) {
+        for (uint32_t l = 0; l < 32; l++) { /* words 4j .. 4j+3 are the four outputs of counter j (orx_state.h) */
             uint32_t ctr[4] = { (uint32_t)(blk * 32 + l), 0u, (uint32_t)s->game, (uint32_t)(s->game >> 32) };
             uint32_t o[4];
             philox4x32_10(ctr, key, o);
-            for (int c = 0; c < 4; c++) s->buf[c * 32 + l] = o[c];
+            for (int c = 0; c < 4; c++) s->buf[4 * l + c] = o[c];
         }
         s->buf_block = blk;
     }
@@ -135,7 +135,10 @@ static double jr_next_double(Stream *s)
     return (double)((hi << 27) + lo) * 0x1.0p-53;
 }
 
-/* StrictMath.log == fdlibm __ieee754_log (e_log.c 1.3 95/01/18), restated. */
+/* StrictMath.log == fdlibm __ieee754_log (e_log.c 1.3 95/01/18), restated.  Algorithm and constants are fdlibm's:
+ *   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *   Developed at SunPro, a Sun Microsystems, Inc. business.  Permission to use, copy, modify, and distribute this
+ *   software is freely granted, provided that this notice is preserved. */
 static double fdlibm_log(double x)
 {
     static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
@@ -604,6 +607,10 @@ typedef struct Board {
     int modellingTurnLimit;
     int moveable[MAXN];       /* Country.getMoveableArmies */
 
+    /* CardManager.random: re-created by simReset on every setupState (O/CardManager.java:245) */
+    int dealMode;             /* ORX_DEAL_* of the leaf record                          */
+    uint64_t dealLcg;         /* java.util.Random's 48-bit state                        */
+
     /* engine bookkeeping */
     Stream rng;
     uint32_t flags;
@@ -655,6 +662,25 @@ static int getRandomSet(Board *b, const CardList *h, int idx[3])
     return 0;
 }
 
+/* java.util.Random itself (the LCG of the JDK documentation): CardManager.random after simReset's
+ * `new Random(simDeck.hashCode())` (O/CardManager.java:245) */
+static void lcg_set_seed(uint64_t *st, int64_t seed) { *st = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); }
+static int32_t lcg_next(uint64_t *st, int bits)
+{
+    *st = (*st * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)(int64_t)(*st >> (48 - bits));
+}
+static int32_t lcg_next_int(uint64_t *st, int32_t bound) /* bound > 0: the deck is not empty */
+{
+    int32_t r = lcg_next(st, 31);
+    int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+    for (int32_t u = r;; u = lcg_next(st, 31)) {
+        r = u % bound;
+        if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
+    }
+}
+
 /* O/CardManager.java:250-263 ; returns 0 when the deck is legitimately empty */
 static int simDeal(Board *b, uint8_t *card)
 {
@@ -662,7 +688,8 @@ static int simDeal(Board *b, uint8_t *card)
         if (!b->canRunOutOfCards) FAIL(b);
         return 0;
     }
-    *card = list_remove_at(&b->simDeck, jr_next_int(&b->rng, b->simDeck.n));
+    *card = list_remove_at(&b->simDeck, b->dealMode == ORX_DEAL_GAME_STREAM ? jr_next_int(&b->rng, b->simDeck.n)
+                                                                           : lcg_next_int(&b->dealLcg, b->simDeck.n));
     b->ct.writes++;
     return 1;
 }
@@ -1356,10 +1383,13 @@ static void setupState(Board *b, const uint8_t *leaf)
         for (int t = 0; t < N && !bad; t++) {
             int o = owner[t];
             if (!(o < P || (o == ORX_OWNER_NONE && h->phase == ORX_PHASE_COUNTRY_SELECTION))) bad = 1;
-            if (armies[t] < 1 || armies[t] > ORX_MAX_ARMIES) bad = 1;
+            /* an INVADE leaf may carry the conquered country at 0 armies (executeInvasion overwrites it) */
+            int lo = (h->phase == ORX_PHASE_ATTACK && h->attack_state == ORX_ATTACK_INVADE && t == h->defending_cc) ? 0 : 1;
+            if (armies[t] < lo || armies[t] > ORX_MAX_ARMIES) bad = 1;
         }
         for (int i = 0; i < (int)h->n_hand + (int)h->n_deck && !bad; i++)
             if (!(cards[i] < N || cards[i] == ORX_CARD_WILD)) bad = 1;
+        if (h->deal_mode != ORX_DEAL_LEAF_LCG && h->deal_mode != ORX_DEAL_GAME_STREAM) bad = 1;
         if (bad) { FAIL(b); return; }
     }
 
@@ -1377,6 +1407,8 @@ static void setupState(Board *b, const uint8_t *leaf)
     b->simDeck.n = 0;
     for (int i = 0; i < h->n_deck; i++) list_add(&b->simDeck, cards[h->n_hand + i]);
     b->simCardProgressionPos = h->card_pos;
+    b->dealMode = h->deal_mode;
+    lcg_set_seed(&b->dealLcg, (int64_t)h->deal_seed); /* random = new Random(simDeck.hashCode()) :245 */
     for (int p = 0; p < b->P; p++) {
         b->playerCards[p].n = 0;
         if (p == b->currentPlayer) {

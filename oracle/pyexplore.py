@@ -77,10 +77,7 @@ class ExplorationBoard:
         self.moveable = list(moveable); self.fortified = list(fortified) if fortified is not None else [0] * N
         self.real_hand, self.real_deck, self.real_pos = list(bs.hand), list(bs.deck), bs.cardProgressionPos
         self.deck = list(self.real_deck); self.card_pos = self.real_pos
-        h = 1469598103934665603
-        for c in self.deck:
-            h ^= c; h = (h * 1099511628211) & ((1 << 64) - 1)
-        self.rnd = JavaRandom(h)
+        self.rnd = JavaRandom(bs.deal_seed(self.deck))   # new Random(simDeck.hashCode()) (CardManager.java:245)
         self.cards = [[] for _ in range(P)]
         for p in range(P):
             if p == self.cp:

@@ -121,8 +121,45 @@ def modelled():
     print("classic42_mid_s1_modelled", games.shape)
 
 
+def results_only():
+    """Round 2: the stream layout and the deal generator changed (include/orx_state.h), the LEAVES did not.  Keeps the
+    committed leaf files (the bench workload stays the same mid-game position), stamps each record's deal_seed with
+    deck_hash(deck) -- the stand-in for simDeck.hashCode() -- and regenerates every per-game golden from them."""
+    from oponn_b200.state import BoardState, leaf_layout
+    out = {}
+    old = dict(np.load(os.path.join(HERE, "golden_games.npz")))
+    m, r = classic42(6), Rules()
+
+    def stamp(path, mp):
+        L = leaf_layout(mp.n_territories, mp.n_players)
+        a = np.fromfile(path, dtype=np.uint8).reshape(-1, L.stride)
+        for i in range(len(a)):
+            bs = BoardState.unpack(mp, a[i]); bs.dealSeed = None; bs.dealFromStream = False
+            a[i] = bs.pack(mp)
+        a.tofile(path)
+        return a
+
+    leaf = stamp(os.path.join(HERE, "classic42_mid_s1.leaf"), m)[0]
+    leaves = stamp(os.path.join(HERE, "classic42_mid_64.leaves"), m)
+    o = Oracle(m, r)
+    out["classic42_mid_s1"] = o.rollout_batch(leaf[None, :], 512, RUN_SEED, per_game=True, threads=8)[1]
+    out["classic42_mid_64"] = o.rollout_batch(leaves, 4, RUN_SEED, per_game=True, threads=8)[1]
+    out["classic42_mid_64_seeds"] = old["classic42_mid_64_seeds"]
+    o.close()
+    m2, r2 = synth200(), Rules(max_player_turns=4096)
+    leaf2 = stamp(os.path.join(HERE, "synth200_mid_s1.leaf"), m2)[0]
+    o2 = Oracle(m2, r2)
+    out["synth200_mid_s1"] = o2.rollout_batch(leaf2[None, :], 64, RUN_SEED, per_game=True, threads=8)[1]
+    o2.close()
+    np.savez_compressed(os.path.join(HERE, "golden_games.npz"), **out)
+    modelled()
+    workload()
+
+
 if __name__ == "__main__":
-    if "--workload" in sys.argv:
+    if "--results" in sys.argv:
+        results_only()
+    elif "--workload" in sys.argv:
         workload()
     elif "--modelled" in sys.argv:
         modelled()

@@ -14,13 +14,13 @@ def test_philox_known_answers():
 
 
 def test_counter_stream_layout():
-    """word i = Philox(ctr = {32*(i/128) + i%32, 0, game_lo, game_hi}, key = seed)[(i/32) % 4] (orx_state.h)"""
+    """word i = Philox(ctr = {i/4, 0, game_lo, game_hi}, key = seed)[i % 4] (orx_state.h)"""
     seed, game = 0x1122334455667788, 0x99AABBCCDDEEFF00
     vals, pos, flags = pyoracle.stream_draws([-2] * 300, seed=seed, game=game)
     key = [seed & 0xFFFFFFFF, seed >> 32]
     for i in (0, 1, 31, 32, 95, 127, 128, 200, 299):
-        ctr = [32 * (i // 128) + i % 32, 0, game & 0xFFFFFFFF, game >> 32]
-        assert int(vals[i]) == pyoracle.philox4x32_10(ctr, key)[(i // 32) % 4]
+        ctr = [i // 4, 0, game & 0xFFFFFFFF, game >> 32]
+        assert int(vals[i]) == pyoracle.philox4x32_10(ctr, key)[i % 4]
     assert pos == 300 and flags == 0
 
 
