@@ -55,6 +55,9 @@ int main(int argc, char **argv)
         for (int t = 0; t < N; t++) { leaf[L.off_owner + t] = (uint8_t)(t % P); armies[t] = 3; }
         for (int i = 0; i < N; i++) leaf[L.off_cards + i] = (uint8_t)i;
         leaf[L.off_cards + N] = ORX_CARD_WILD; leaf[L.off_cards + N + 1] = ORX_CARD_WILD;
+        /* CardManager.simReset re-seeds its generator from simDeck.hashCode() (CardManager.java:245): a Java host
+         * passes that value; without a JVM the deck hash of orx_state.h stands in for it */
+        h->deal_mode = ORX_DEAL_LEAF_LCG; h->deal_seed = orx_deck_hash(leaf + L.off_cards, N + 2);
     }
     const int playouts = argc > 2 ? atoi(argv[2]) : 4096;
     const uint64_t seed = argc > 3 ? strtoull(argv[3], NULL, 10) : 20261019ull;

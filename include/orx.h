@@ -99,6 +99,12 @@ void *orx_stream(OrxCtx *ctx);
 float    orx_last_kernel_ms(OrxCtx *ctx);
 uint64_t orx_kernel_launches(const OrxCtx *ctx);
 
+/* Which rollout kernel the last launch of this context used: 1 = warp-per-game (orx_game.cuh: any map, replay
+ * streams, modelled opponents, small batches), 2 = lane-per-game (orx_lanes.cuh: all-SimRandom counter-stream batches
+ * of at least ~4 games per resident lane on maps up to 64 territories), 0 = none yet.  Both produce identical
+ * records; the environment variable ORX_KERNEL=warp|lanes overrides the choice (tests, profiling). */
+int orx_last_kernel_kind(const OrxCtx *ctx);
+
 /* Replaces: BattleSim.getAttackOutcomes(a, d) (BattleSim.java:174-184) for 1 <= a,d <= 100.
  * Rows are in the reference's order (descending probability, stable).  Returns the row count
  * (<= a+d) or a negative error; arrays hold up to `cap` rows. */

@@ -18,6 +18,8 @@
 
 #include "../../include/orx.h"
 #include "orx_game.cuh"
+#include "orx_lanes.cuh"
+#include "orx_mapimage.h"
 
 using namespace orx;
 
@@ -195,6 +197,13 @@ struct OrxCtx {
     int sm_count = 0;
     int blocks_per_sm[4] = { 0, 0, 0, 0 };  // [replay + 2 * modelling]
     bool modelling = false;           // orx_set_sim_agents: the MODEL kernels run, the slice carries moveable armies
+    // the lane-per-game kernel (orx_lanes.cuh): all-SimRandom, counter streams, <= 64 territories, large batches
+    int lane_blocks_per_sm = 0;
+    size_t lane_smem_bytes = 0;
+    unsigned long long lane_min_total = 0;   // batches at least this large go to the lane kernel
+    int kernel_choice = 0;                   // ORX_KERNEL: 0 auto, 1 always warp-per-game, 2 lane-per-game whenever eligible
+    LaneTune lane_tune;
+    int last_kernel = 0;                     // 1 warp-per-game, 2 lane-per-game (orx_last_kernel_kind)
     int blocks_cap = 0;               // ORX_BLOCKS_PER_SM tuning knob
     size_t smem_bytes = 0;
     uint8_t *d_blob = nullptr;
@@ -230,43 +239,6 @@ static int ensure(void **p, size_t *cap, size_t need)
     CK(cudaMalloc(p, need));
     *cap = need;
     return ORX_OK;
-}
-
-// CardManager.getCardCashValue families (O/CardManager.java:283-341)
-static int parse_progression(const char *cp, double *exp_out, int *five)
-{
-    *exp_out = 1.0; *five = 0;
-    if (!cp) return PROG_UNKNOWN;
-    if (strchr(cp, '%')) {
-        const char *hat = strchr(cp, '^');
-        int pct = 0;
-        if (hat) {  // Integer.valueOf(cp.substring(cp.indexOf('^')+1, cp.length()-1))
-            std::string t(hat + 1);
-            if (!t.empty()) t.pop_back();
-            pct = atoi(t.c_str());
-        }
-        *five = cp[0] == '5';
-        *exp_out = 1 + (pct / 100.0);
-        return PROG_TABLE;
-    }
-    if (!strcmp(cp, "0")) return PROG_0;
-    if (!strcmp(cp, "5, 5, 5...")) return PROG_555;
-    if (!strcmp(cp, "4, 4, 6, 6, 6, 8, 8, 8, 8, 10...")) return PROG_4466688;
-    if (!strcmp(cp, "4, 5, 6...")) return PROG_456;
-    if (!strcmp(cp, "4, 6, 8...")) return PROG_468;
-    if (!strcmp(cp, "3, 6, 9...")) return PROG_369;
-    if (!strcmp(cp, "4, 6, 8, 10, 15, 20...")) return PROG_46810;
-    if (!strcmp(cp, "5, 10, 15...")) return PROG_51015;
-    if (!strcmp(cp, "4, 6, 8, 10, 15, 20, 25, 10, 10, 10...")) return PROG_4681015202510;
-    return PROG_UNKNOWN;
-}
-
-static int32_t java_d2i_host(double d)
-{
-    if (d != d) return 0;
-    if (d >= 2147483647.0) return 2147483647;
-    if (d <= -2147483648.0) return (int32_t)(-2147483647 - 1);
-    return (int32_t)d;
 }
 
 typedef void (*RolloutKernel)(const DevMap, const RolloutArgs);
@@ -317,26 +289,47 @@ static int configure_context(OrxCtx *c)
     return ORX_OK;
 }
 
+// the lane-per-game kernel: shared memory per block, residency, scheduler tuning, and the batch size from which it
+// is used (below that the warp-per-game kernel fills the machine better: a batch needs 32 games per warp here)
+static int configure_lanes(OrxCtx *c)
+{
+    c->lane_blocks_per_sm = 0;
+    if (c->dm.N > LN_MAXN) return ORX_OK;
+    const LaneLayout LL = lane_layout(c->dm.N, c->dm.P);
+    c->lane_smem_bytes = (size_t)c->dm.blob_bytes + (size_t)(ORX_LANE_THREADS / 32) * (size_t)LL.words * 128u;
+    CK(cudaFuncSetAttribute((const void *)rollout_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lane_smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->lane_blocks_per_sm, (const void *)rollout_lanes_kernel, ORX_LANE_THREADS, c->lane_smem_bytes));
+    if (const char *lim = getenv("ORX_LANE_BLOCKS_PER_SM")) { int v = atoi(lim); if (v >= 1 && v < c->lane_blocks_per_sm) c->lane_blocks_per_sm = v; }
+    LaneTune &t = c->lane_tune;
+    memset(&t, 0, sizeof t);
+    t.thr_new = 4; t.thr_turn = 8; t.thr_sel = 8; t.thr_fin = 8;
+    t.age_new = 64; t.age_turn = 32; t.age_sel = 8; t.age_fin = 8;
+    t.coop_min = 48;
+    if (const char *tv = getenv("ORX_LANE_TUNE")) {   // "thr_new,thr_turn,thr_sel,thr_fin,age_new,age_turn,age_sel,age_fin,coop_min"
+        int v[9], n = sscanf(tv, "%d,%d,%d,%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8);
+        int32_t *dst[9] = { &t.thr_new, &t.thr_turn, &t.thr_sel, &t.thr_fin, &t.age_new, &t.age_turn, &t.age_sel, &t.age_fin, &t.coop_min };
+        for (int i = 0; i < n && i < 9; i++) *dst[i] = v[i];
+    }
+    // auto: at least 4 games per resident lane, so that the tail of a launch (lanes running dry) stays small
+    c->lane_min_total = 4ull * (unsigned long long)c->sm_count * (unsigned long long)c->lane_blocks_per_sm * ORX_LANE_THREADS;
+    if (const char *k = getenv("ORX_KERNEL")) c->kernel_choice = !strcmp(k, "warp") ? 1 : (!strcmp(k, "lanes") ? 2 : 0);
+    if (const char *mt = getenv("ORX_LANE_MIN_TOTAL")) c->lane_min_total = strtoull(mt, nullptr, 10);
+    return ORX_OK;
+}
+
+static bool use_lane_kernel(const OrxCtx *c, bool replay, const RolloutArgs &ar)
+{
+    if (replay || c->modelling || c->lane_blocks_per_sm < 1 || c->kernel_choice == 1) return false;
+    if (ar.total >= (1ull << 32)) return false;
+    return c->kernel_choice == 2 || ar.total >= c->lane_min_total;
+}
+
 extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, OrxCtx **out)
 {
     if (!map || !rules || !out) return set_err(ORX_E_INVALID, "null argument");
     *out = nullptr;
-    const int N = map->n_territories, C = map->n_continents, P = map->n_players;
-    if (N < 1 || N > ORX_MAX_TERRITORIES || P < 2 || P > ORX_MAX_PLAYERS || C < 1 || C > ORX_MAX_CONTINENTS)
-        return set_err(ORX_E_INVALID, "map dimensions out of range");
-    if (!map->adj_offsets || !map->adj || !map->continent || !map->continent_bonus)
-        return set_err(ORX_E_INVALID, "map arrays missing");
-    int maxdeg = 0;
-    if (map->adj_offsets[0] != 0) return set_err(ORX_E_INVALID, "adj_offsets[0] != 0");
-    for (int t = 0; t < N; t++) {
-        int dg = map->adj_offsets[t + 1] - map->adj_offsets[t];
-        if (dg < 0 || dg > ORX_MAX_DEGREE) return set_err(ORX_E_INVALID, "territory degree out of range");
-        if (dg > maxdeg) maxdeg = dg;
-        for (int e = map->adj_offsets[t]; e < map->adj_offsets[t + 1]; e++)
-            if (map->adj[e] < 0 || map->adj[e] >= N) return set_err(ORX_E_INVALID, "neighbour code out of range");
-        if (map->continent[t] < 0 || map->continent[t] >= C) return set_err(ORX_E_INVALID, "continent id out of range");
-        if (map->card_symbol && (map->card_symbol[t] < 0 || map->card_symbol[t] > 2)) return set_err(ORX_E_INVALID, "card symbol out of range");
-    }
+    MapImage im;
+    if (const char *why = build_map_image(map, rules, im)) return set_err(ORX_E_INVALID, "%s", why);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(ORX_E_CUDA, "no CUDA device: this engine has no CPU path");
@@ -345,65 +338,12 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
 
     OrxCtx *c = new OrxCtx();
     c->device = device;
+    c->dm = im.dm;
+    c->nwt = im.nwt;
     DevMap &dm = c->dm;
-    memset(&dm, 0, sizeof dm);
-    c->nwt = N <= 64 ? 2 : 8;
-    dm.N = N; dm.C = C; dm.P = P; dm.NW = c->nwt; dm.NP = 32 * c->nwt;
-    dm.degp = ((maxdeg > 0 ? maxdeg : 1) + 3) & ~3;
-    dm.cap = (N + 2 + 31) & ~31;
-    dm.use_cards = rules->use_cards != 0; dm.transfer_cards = rules->transfer_cards != 0;
-    dm.cont_inc = rules->continent_increase;
-    dm.max_turns = rules->max_player_turns > 0 ? rules->max_player_turns : (1 << 16);
-    dm.can_run_out = P * 5 > N + 2;  // O/CardManager.java:65
-    double pexp; int five;
-    dm.prog_family = parse_progression(rules->card_progression, &pexp, &five);
-    {   // calculateStartingArmies (SimulationBoard.java:518-533)
-        double f1 = N / 42.0; f1 -= 1.0; f1 /= 2.0; f1 += 1.0;
-        dm.start_armies = (int)floor(f1 * (50 - P * 5) + 0.5);
-    }
-    OrxLeafLayout L = orx_leaf_layout(N, P);
-    dm.leaf_stride = L.stride; dm.off_owner = L.off_owner; dm.off_armies = L.off_armies;
-    dm.off_ncards = L.off_ncards; dm.off_cards = L.off_cards;
-
-    // static map image
-    int off = 0;
-    dm.adj_off = off;  off += (N * dm.degp + 3) & ~3;
-    dm.deg_off = off;  off += dm.NP;
-    dm.sym_off = off;  off += dm.NP;
-    dm.nbr_off = off;  off += 4 * dm.NW * dm.NP;
-    dm.cont_off = off; off += 4 * C * dm.NW;
-    dm.bonus_off = off; off += 4 * C;
-    dm.blob_bytes = (off + 15) & ~15;
-    std::vector<uint8_t> blob((size_t)dm.blob_bytes, 0);
-    uint32_t *nbr = (uint32_t *)(blob.data() + dm.nbr_off), *cont = (uint32_t *)(blob.data() + dm.cont_off);
-    int32_t *bonus = (int32_t *)(blob.data() + dm.bonus_off);
-    for (int t = 0; t < N; t++) {
-        int dg = map->adj_offsets[t + 1] - map->adj_offsets[t];
-        blob[dm.deg_off + t] = (uint8_t)dg;
-        for (int j = 0; j < dg; j++) {
-            int x = map->adj[map->adj_offsets[t] + j];
-            blob[dm.adj_off + t * dm.degp + j] = (uint8_t)x;
-            nbr[(x >> 5) * dm.NP + t] |= 1u << (x & 31);
-        }
-        int sym = map->card_symbol ? map->card_symbol[t] : t % 3;  // O/CardManager.java:54-61
-        blob[dm.sym_off + t] = (uint8_t)(1u << sym);
-        cont[map->continent[t] * dm.NW + (t >> 5)] |= 1u << (t & 31);
-    }
-    for (int i = 0; i < C; i++) bonus[i] = map->continent_bonus[i];
-
+    const std::vector<uint8_t> &blob = im.blob;
     layout_slice(c, false);
     dm.model_limit = 0; dm.agents = 0u;
-
-    // single-roll thresholds: floor(cdf * 2^53) of O/BattleSim.java:36-44 (float sums widened to double)
-    {
-        const float a1_d1_al0 = 0.4167f, a1_d2_al0 = 0.2546f, a2_d1_al0 = 0.5787f, a2_d2_al0 = 0.2276f, a2_d2_al1 = 0.3241f,
-                    a3_d1_al0 = 0.6597f, a3_d2_al0 = 0.3717f, a3_d2_al1 = 0.3358f;
-        const double rows[6][2] = { { a1_d1_al0, 1.0 }, { a1_d2_al0, 1.0 }, { a2_d1_al0, 1.0 },
-                                    { a2_d2_al0, (float)(a2_d2_al0 + a2_d2_al1) }, { a3_d1_al0, 1.0 },
-                                    { a3_d2_al0, (float)(a3_d2_al0 + a3_d2_al1) } };
-        for (int r = 0; r < 6; r++)
-            for (int k = 0; k < 2; k++) dm.single_thr[r][k] = (uint64_t)(rows[r][k] * 9007199254740992.0);
-    }
 
 #define CKC(call)                                                                                         \
     do {                                                                                                  \
@@ -426,25 +366,14 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
     CKC(cudaMalloc(&c->d_blob, blob.size()));
     CKC(cudaMemcpyAsync(c->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
     dm.blob = c->d_blob;
-    if (dm.cont_inc != 0) {  // recalculateContinentBonuses (SimulationBoard.java:956-963), one row per exponent
-        std::vector<int32_t> tab((size_t)ORX_BONUS_ROUNDS * C);
-        for (int e = 0; e < ORX_BONUS_ROUNDS; e++) {
-            double factor = pow(1 + dm.cont_inc / 100.0, (double)e);
-            for (int i = 0; i < C; i++) tab[(size_t)e * C + i] = java_d2i_host(floor(map->continent_bonus[i] * factor));
-        }
-        CKC(cudaMalloc(&c->d_bonus_table, tab.size() * 4));
-        CKC(cudaMemcpy(c->d_bonus_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    if (!im.bonus_table.empty()) {
+        CKC(cudaMalloc(&c->d_bonus_table, im.bonus_table.size() * 4));
+        CKC(cudaMemcpy(c->d_bonus_table, im.bonus_table.data(), im.bonus_table.size() * 4, cudaMemcpyHostToDevice));
         dm.bonus_table = c->d_bonus_table;
     }
-    if (dm.prog_family == PROG_TABLE) {  // exponential progressions (O/CardManager.java:287-305)
-        std::vector<int32_t> tab(ORX_CARD_VALUES);
-        for (int pos = 0; pos < ORX_CARD_VALUES; pos++) {
-            int base, offset;
-            if (five) { base = 5 * pos; offset = 6; } else { base = pos <= 4 ? 2 * (pos + 1) : 5 * (pos - 2); offset = 8; }
-            tab[pos] = java_d2i_host(floor(base <= 25 ? (double)base : base * pow(pexp, (double)(pos - offset))));
-        }
-        CKC(cudaMalloc(&c->d_card_table, tab.size() * 4));
-        CKC(cudaMemcpy(c->d_card_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    if (!im.card_table.empty()) {
+        CKC(cudaMalloc(&c->d_card_table, im.card_table.size() * 4));
+        CKC(cudaMemcpy(c->d_card_table, im.card_table.data(), im.card_table.size() * 4, cudaMemcpyHostToDevice));
         dm.card_table = c->d_card_table;
     }
     CKC(cudaMalloc(&c->d_meta, sizeof(uint32_t) * ORX_TABLE_LIMIT * ORX_TABLE_LIMIT));
@@ -462,6 +391,7 @@ extern "C" int orx_create(const OrxMap *map, const OrxRules *rules, int device, 
     }
     if (const char *lim = getenv("ORX_BLOCKS_PER_SM")) c->blocks_cap = atoi(lim);  // tuning knob: cap the resident blocks per SM
     if (configure_context(c) != ORX_OK) { orx_destroy(c); return ORX_E_CUDA; }
+    if (configure_lanes(c) != ORX_OK) { orx_destroy(c); return ORX_E_CUDA; }
     CKC(cudaStreamSynchronize(c->stream));
 #undef CKC
     *out = c;
@@ -511,6 +441,7 @@ extern "C" int orx_set_sim_agents(OrxCtx *c, const int32_t *agent_ids, int model
     return configure_context(c);
 }
 
+extern "C" int orx_last_kernel_kind(const OrxCtx *c) { return c ? c->last_kernel : 0; }
 extern "C" int orx_leaf_stride(const OrxCtx *c) { return c ? c->dm.leaf_stride : ORX_E_INVALID; }
 extern "C" void *orx_stream(OrxCtx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t orx_kernel_launches(const OrxCtx *c) { return c ? c->launches : 0; }
@@ -539,6 +470,33 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStr
     const bool timed = stream == nullptr;
     if (!stream) stream = c->stream;
     CK(cudaMemsetAsync(ar.ticket, 0, sizeof(unsigned long long), stream));
+    if (use_lane_kernel(c, replay, ar)) {
+        LaneArgs la;
+        memset(&la, 0, sizeof la);
+        la.leaves = ar.leaves; la.n_leaves = ar.n_leaves; la.playouts_per_leaf = ar.playouts_per_leaf; la.total = ar.total;
+        la.seed = ar.seed; la.first_game = ar.first_game; la.agg = ar.agg; la.games = ar.games; la.ticket = ar.ticket;
+        for (int r = 0; r < 10; r++) {
+            la.rk[2 * r] = (uint32_t)ar.seed + (uint32_t)r * 0x9E3779B9u;
+            la.rk[2 * r + 1] = (uint32_t)(ar.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+        }
+        la.tune = c->lane_tune;
+        unsigned long long blocks = (unsigned long long)c->sm_count * (unsigned long long)c->lane_blocks_per_sm;
+        const unsigned long long need = (ar.total + ORX_LANE_THREADS - 1) / ORX_LANE_THREADS;
+        if (need < blocks) blocks = need;
+        if (blocks == 0) blocks = 1;
+        {
+            cudaError_t e = cudaFuncSetAttribute((const void *)rollout_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lane_smem_bytes);
+            if (e != cudaSuccess) return set_err(ORX_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        if (timed) CK(cudaEventRecord(c->ev0, stream));
+        rollout_lanes_kernel<<<dim3((unsigned)blocks), dim3(ORX_LANE_THREADS), c->lane_smem_bytes, stream>>>(c->dm, la);
+        CK(cudaGetLastError());
+        if (timed) { CK(cudaEventRecord(c->ev1, stream)); c->have_time = true; }
+        c->launches++;
+        c->last_kernel = 2;
+        return ORX_OK;
+    }
+    c->last_kernel = 1;
     const RolloutKernel kern = kernel_for(c->nwt, replay, c->modelling);
     unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[(int)replay + 2 * (int)c->modelling] * (ORX_BLOCK_THREADS / 32);
     unsigned long long need = (ar.total + (ORX_BLOCK_THREADS / 32) - 1) / (ORX_BLOCK_THREADS / 32);
