@@ -31,6 +31,7 @@
 #include <math.h>
 #include <string.h>
 #define LN_M inline
+#define LN_NOUNROLL
 #define LN_COLD inline
 #define LN_NOINLINE static inline
 #define LN_LDG(p) (*(p))
@@ -38,6 +39,7 @@ extern "C" double orc_fdlibm_log(double);   // the oracle's fdlibm restatement (
 #else
 #include "orx_device.cuh"
 #define LN_M __device__ __forceinline__
+#define LN_NOUNROLL _Pragma("unroll 1")
 #define LN_COLD __device__ __noinline__       // once-per-turn code: out of line, called on a memory copy of the lane (see the kernel)
 #define LN_NOINLINE static __device__ __noinline__
 #define LN_LDG(p) __ldg(p)
@@ -46,7 +48,7 @@ extern "C" double orc_fdlibm_log(double);   // the oracle's fdlibm restatement (
 namespace orx {
 
 // lane states: the section a lane waits for
-enum { LS_NEW = 0, LS_TURN = 1, LS_SEL = 2, LS_DICE = 3, LS_FIN = 4, LS_COOP = 5, LS_EXIT = 6, LS_GAUSS = 7 };
+enum { LS_NEW = 0, LS_TURN = 1, LS_SEL = 2, LS_DICE = 3, LS_FIN = 4, LS_COOP = 5, LS_EXIT = 6, LS_GAUSS = 7, LS_ELIM = 8 };
 
 // bits of Lane::fl above the ORX_FLAG_* bits
 #define LF_INVADED   0x100u   // hasInvadedACountry
@@ -95,7 +97,7 @@ static inline ORX_HD LaneLayout lane_layout(int N, int P)
     L.POT = w;   w += P;                          // int32 playerOutOnTurn[P]
     L.PC = w;    w += 2;                          // uint8 playerCountries[P]
     L.NC = w;    w += 3;                          // uint8 list lengths [P + 1]
-    L.RING = w;  w += 8;                          // the next (at most 8) stream words
+    L.RING = w;  w += 16;                         // the next (at most 11) stream words, word i in slot i % 16
     L.GAUSS = w; w += 2;                          // nextNextGaussian
     L.words = w;
     return L;
@@ -237,41 +239,44 @@ struct Lane : LaneEnv, LaneState {
 
     // ---- ordered lists: list li < P is player li's hand, li == P the sim deck ------------
     LN_M uint8_t *list(int li) const { return cards + li * LN_CAP; }
-    LN_M void list_add(int li, int card)
+    LN_COLD void list_add(int li, int card)
     {
         int n = ncard(li);
         if (n >= dm->N + 2) { fail(); return; }
         list(li)[n] = (uint8_t)card;
         set_ncard(li, n + 1);
     }
-    LN_M int list_remove_at(int li, int i)
+    LN_COLD int list_remove_at(int li, int i)
     {
         uint8_t *p = list(li);
         int n = ncard(li), c = p[i];
+        LN_NOUNROLL
         for (int k = i; k < n - 1; k++) p[k] = p[k + 1];
         set_ncard(li, n - 1);
         return c;
     }
 
     // ---- the word stream (orx_state.h): word i = Philox(ctr = {i / 4, 0, game}, key = seed)[i % 4] ------------
-    // The ring holds words [pos, lim); lim is a multiple of 4 and lim - pos <= 7.
+    // The ring holds words [pos, lim); lim is a multiple of 4 and lim - pos <= 11.
     LN_M void gen()
     {
         uint32_t o[4];
         ln_philox(lim >> 2, g0, g1, ar->rk, o);
-        const int s = oRING + (int)(lim & 4u);
+        const int s = oRING + (int)(lim & 12u);
         stw(s, o[0]); stw(s + 1, o[1]); stw(s + 2, o[2]); stw(s + 3, o[3]);
         lim += 4u;
     }
     LN_M void gen_call()   // the same through an out-of-line Philox (refills outside the hot sections' top-up)
     {
         const LnWords o = ln_philox_call(lim >> 2, g0, g1, ar->rk);
-        const int s = oRING + (int)(lim & 4u);
+        const int s = oRING + (int)(lim & 12u);
         stw(s, o.w0); stw(s + 1, o.w1); stw(s + 2, o.w2); stw(s + 3, o.w3);
         lim += 4u;
     }
-    LN_M void topup() { while ((int)(lim - pos) < 4) gen(); }       // afterwards at least 4 words are buffered (two trips only right after a cooperative battle)
-    LN_M uint32_t word_nc() { uint32_t v = ldw(oRING + (int)(pos & 7u)); pos++; return v; }   // caller knows pos < lim
+    // afterwards at least 8 words are buffered: a SEL trip (2 words) followed by a DICE trip (4) never runs dry, and the
+    // FIN section checks (usually one Philox per loop trip; up to three right after a cooperative battle)
+    LN_M void topup() { while ((int)(lim - pos) < 8) gen(); }
+    LN_M uint32_t word_nc() { uint32_t v = ldw(oRING + (int)(pos & 15u)); pos++; return v; }   // caller knows pos < lim
     LN_M uint32_t word() { if ((int)(lim - pos) <= 0) gen_call(); return word_nc(); }
 
     // java.util.Random.nextInt(bound) for a bound the caller knows to be in 1..255: u % bound by multiplication with
@@ -282,6 +287,7 @@ struct Lane : LaneEnv, LaneState {
         uint32_t u = (CHECKED ? word() : word_nc()) >> 1;
         const uint32_t b = (uint32_t)bound, m = b - 1u;
         if ((b & m) == 0u) return (int)(((unsigned long long)b * u) >> 31);
+        LN_NOUNROLL
         for (;;) {
             uint32_t q = ln_umulhi(u, mapw(dm->magic_off + 4 * (int)b));
             uint32_t r = u - q * b;
@@ -291,12 +297,26 @@ struct Lane : LaneEnv, LaneState {
         }
     }
     // java.util.Random.nextInt(bound), any bound
-    LN_M int next_int(int bound)
+    LN_COLD int next_int(int bound)
     {
         if (bound <= 0) { fail(); return 0; }
         uint32_t u = word() >> 1;
         const uint32_t b = (uint32_t)bound, m = b - 1u;
         if ((b & m) == 0u) return (int)(((unsigned long long)b * u) >> 31);
+        LN_NOUNROLL
+        for (;;) {
+            uint32_t r = u % b;
+            if ((int)(u - r + m) >= 0) return (int)r;
+            u = word() >> 1;
+        }
+    }
+    // the same, inline, for the hot sections (bound > 0)
+    LN_M int next_int_hot(int bound)
+    {
+        uint32_t u = word() >> 1;
+        const uint32_t b = (uint32_t)bound, m = b - 1u;
+        if ((b & m) == 0u) return (int)(((unsigned long long)b * u) >> 31);
+        LN_NOUNROLL
         for (;;) {
             uint32_t r = u % b;
             if ((int)(u - r + m) >= 0) return (int)r;
@@ -312,7 +332,7 @@ struct Lane : LaneEnv, LaneState {
     }
     LN_M double next_double() { return (double)(long long)next_k53<true>() * 0x1.0p-53; }
     // java.util.Random.nextGaussian(): polar method, second value cached per playout
-    LN_M double next_gaussian()
+    LN_COLD double next_gaussian()
     {
         if (fl & LF_GAUSS) {
             fl &= ~LF_GAUSS;
@@ -322,6 +342,7 @@ struct Lane : LaneEnv, LaneState {
             return g;
         }
         double v1, v2, q;
+        LN_NOUNROLL
         do {
             v1 = LN_DSUB(LN_DMUL(2.0, next_double()), 1.0);
             v2 = LN_DSUB(LN_DMUL(2.0, next_double()), 1.0);
@@ -342,18 +363,19 @@ struct Lane : LaneEnv, LaneState {
 
     // ---- CardManager.random = new Random(simDeck.hashCode()) (O/CardManager.java:245) ----------------------
     LN_M int deal_next31() { deal = (deal * 0x5DEECE66Dull + 0xBull) & ((1ull << 48) - 1ull); return (int)(deal >> 17); }
-    LN_M int deal_next_int(int bound)   // bound > 0
+    LN_COLD int deal_next_int(int bound)   // bound > 0
     {
         int r = deal_next31();
         const int m = bound - 1;
         if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+        LN_NOUNROLL
         for (int u = r;; u = deal_next31()) {
             r = u % bound;
             if ((int)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
         }
     }
     // CardManager.simDeal (:250-263); -1 when the deck is legitimately empty
-    LN_M int sim_deal()
+    LN_COLD int sim_deal()
     {
         const int n = ncard(dm->P);
         if (n == 0) { if (!dm->can_run_out) fail(); return -1; }
@@ -369,6 +391,7 @@ struct Lane : LaneEnv, LaneState {
         const int n = (int)(meta & 0xFFu);
         const uint64_t key = k << 11;
         int lo = 0, hi = n;   // first index whose row takes the key
+        LN_NOUNROLL
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
             if (key <= LN_LDG(rows + mid)) hi = mid; else lo = mid + 1;
@@ -409,6 +432,7 @@ struct Lane : LaneEnv, LaneState {
     {
         if (attackers > 500 && defenders > 500) { gaussian_battle(attackers, defenders, alOut, dlOut); return; }
         int a = attackers, d = defenders;
+        LN_NOUNROLL
         while ((a > 100 || d > 100) && a > 0 && d > 0) {
             const int pa = a < 3 ? a : 3, pd = d < 2 ? d : 2, n = pa < pd ? pa : pd;
             const int x = single_roll(pa, pd, next_k53<true>());
@@ -427,14 +451,17 @@ struct Lane : LaneEnv, LaneState {
     // DECLARED ASSUMPTION (orx_state.h): wildcard, or all equal, or all distinct
     static LN_M bool is_set_bits(uint32_t m) { return (m & 8u) || ln_popc(m) != 2; }
     // number of valid triples i<j<k of the current player's hand; with pick >= 0 also the pick-th one (lexicographic)
-    LN_M int scan_sets(int n, int pick, int idx[3]) const
+    LN_COLD int scan_sets(int n, int pick, int idx[3]) const
     {
         const uint8_t *h = list(cp);
         int count = 0;
+        LN_NOUNROLL
         for (int i = 0; i < n - 2; i++) {
             const uint32_t si = symbit(h[i]);
+            LN_NOUNROLL
             for (int j = i + 1; j < n - 1; j++) {
                 const uint32_t sij = si | symbit(h[j]);
+                LN_NOUNROLL
                 for (int k = j + 1; k < n; k++)
                     if (is_set_bits(sij | symbit(h[k]))) {
                         if (count == pick) { idx[0] = i; idx[1] = j; idx[2] = k; }
@@ -444,7 +471,7 @@ struct Lane : LaneEnv, LaneState {
         }
         return count;
     }
-    LN_M int card_cash_value(int pos_)
+    LN_COLD int card_cash_value(int pos_)
     {
         switch (dm->prog_family) {
         case PROG_0: return 0;
@@ -453,7 +480,9 @@ struct Lane : LaneEnv, LaneState {
             long long v = 8ll * pos_ + 9ll;
             if (v <= 0) return 0;
             long long k = (long long)((sqrt((double)v) - 1.0) * 0.5);
+            LN_NOUNROLL
             while ((2 * k + 1) * (2 * k + 1) >= v && k > 0) k--;
+            LN_NOUNROLL
             while ((2 * k + 1) * (2 * k + 1) < v) k++;
             return (int)(2 * k);
         }
@@ -470,7 +499,7 @@ struct Lane : LaneEnv, LaneState {
         }
     }
     // SimulationBoard.cashCards (:577-618) for hand positions i<j<k
-    LN_M void cash_cards(const int idx[3])
+    LN_COLD void cash_cards(const int idx[3])
     {
         const uint8_t *h = list(cp);
         const int c0 = h[idx[0]], c1 = h[idx[1]], c2 = h[idx[2]];
@@ -479,6 +508,7 @@ struct Lane : LaneEnv, LaneState {
         placeable += card_cash_value(cardpos);
         cardpos++;
         const int cs[3] = { c0, c1, c2 };
+        LN_NOUNROLL
         for (int q = 0; q < 3; q++)
             if (cs[q] != (int)ORX_CARD_WILD && owner(cs[q]) == cp) set_armies(cs[q], armies(cs[q]) + 2);
     }
@@ -500,6 +530,7 @@ struct Lane : LaneEnv, LaneState {
     // SimulationBoard.tearDownCardsPhase (:620-638)
     LN_COLD void tear_down_cards_phase()
     {
+        LN_NOUNROLL
         for (;;) {
             const int n = ncard(cp);
             if (n <= 4 || bad()) break;
@@ -514,22 +545,26 @@ struct Lane : LaneEnv, LaneState {
     }
 
     // ---- board scans ---------------------------------------------------------------------------------------
-    LN_M void compute_mine()
+    LN_COLD void compute_mine()
     {
         uint32_t lo = 0, hi = 0;
         const int N = dm->N;
+        LN_NOUNROLL
         for (int t = 0; t < N && t < 32; t++) lo |= (uint32_t)(owner(t) == cp) << t;
+        LN_NOUNROLL
         for (int t = 32; t < N; t++) hi |= (uint32_t)(owner(t) == cp) << (t - 32);
         mine_lo = lo; mine_hi = hi;
     }
     // owned territories with at least one out-neighbour not owned (SimRandom.java:68-82,250-262)
-    LN_M void border_mask(uint32_t &blo, uint32_t &bhi) const
+    LN_COLD void border_mask(uint32_t &blo, uint32_t &bhi) const
     {
         blo = 0; bhi = 0;
+        LN_NOUNROLL
         for (uint32_t m = mine_lo; m; m &= m - 1u) {
             const int t = ln_ffs(m) - 1;
             if ((nbr_lo(t) & ~mine_lo) | (nbr_hi(t) & ~mine_hi)) blo |= 1u << t;
         }
+        LN_NOUNROLL
         for (uint32_t m = mine_hi; m; m &= m - 1u) {
             const int t = ln_ffs(m) - 1;
             if ((nbr_lo(32 + t) & ~mine_lo) | (nbr_hi(32 + t) & ~mine_hi)) bhi |= 1u << t;
@@ -549,11 +584,12 @@ struct Lane : LaneEnv, LaneState {
         if (dm->cont_inc != 0 && e >= ORX_BONUS_ROUNDS) fail();
     }
     // getPlayerIncome(currentPlayer) (:1076-1090)
-    LN_M int player_income() const
+    LN_COLD int player_income() const
     {
         const int mycount = pc(cp);
         if (mycount == 0) return 0;
         uint32_t income = (uint32_t)(mycount / 3 < 3 ? 3 : mycount / 3);
+        LN_NOUNROLL
         for (int c = 0; c < dm->C; c++)
             if (((cont_lo(c) & ~mine_lo) | (cont_hi(c) & ~mine_hi)) == 0u) income += (uint32_t)current_bonus(c);
         return (int)income;
@@ -564,6 +600,7 @@ struct Lane : LaneEnv, LaneState {
         uint32_t clo, chi;
         border_mask(clo, chi);
         const int n = ln_popc(clo) + ln_popc(chi);
+        LN_NOUNROLL
         while (n_armies > 0 && !bad()) {
             const int k = 1 + next_int(n_armies);
             const int i = next_int(n);
@@ -577,7 +614,7 @@ struct Lane : LaneEnv, LaneState {
     }
 
     // SimulationBoard.playerDefeated (:843-867)
-    LN_M void player_defeated(int player, int conquerer)
+    LN_COLD void player_defeated(int player, int conquerer)
     {
         remaining--;
         set_pot(player, simTurn);
@@ -587,6 +624,7 @@ struct Lane : LaneEnv, LaneState {
             const int nsrc = ncard(player), ndst = ncard(dst);
             if (ndst + nsrc > dm->N + 2) { fail(); return; }
             const uint8_t *src = list(player); uint8_t *d = list(dst);
+            LN_NOUNROLL
             for (int i = 0; i < nsrc; i++) d[ndst + i] = src[i];
             set_ncard(dst, ndst + nsrc);
             set_ncard(player, 0);
@@ -597,7 +635,7 @@ struct Lane : LaneEnv, LaneState {
         }
     }
     // executeInvasion (:814-825) with SimRandom.moveArmiesIn (SimRandom.java:144-155); armies[A] is read from the board
-    LN_M void invade_catchup(int A, int D)
+    LN_COLD void invade_catchup(int A, int D)
     {
         const int aArm = armies(A), available = aArm - 1;
         if (available == 0) { fail(); return; }
@@ -613,22 +651,27 @@ struct Lane : LaneEnv, LaneState {
     {
         const int N = dm->N, P = dm->P;
         int total = 0;
+        LN_NOUNROLL
         for (int t = 0; t < N; t++) total += armies(t);
         if (total <= 100000) return;
         int maxArmies = 0, maxPlayer = -1;
+        LN_NOUNROLL
         for (int p = 0; p < P; p++) {
             int ps = 0;
+            LN_NOUNROLL
             for (int t = 0; t < N; t++) if (owner(t) == p) ps += armies(t);
             if (ps > maxArmies) { maxPlayer = p; maxArmies = ps; }
         }
+        LN_NOUNROLL
         for (int p = 0; p < P; p++)
             if (pc(p) > 0 && p != maxPlayer) { player_defeated(p, maxPlayer); if (bad()) return; }
     }
     // tearDownFortificationPhase (:965-982) with getNextPlayer (:1102-1111)
-    LN_M void tear_down_fortification_phase()
+    LN_COLD void tear_down_fortification_phase()
     {
         const int P = dm->P;
         int np = cp, guard = 0;
+        LN_NOUNROLL
         do { np = np + 1 == P ? 0 : np + 1; if (++guard > P) { fail(); return; } } while (pc(np) == 0);
         if (np < cp) { simTurn++; recalculate_bonuses(); }
         cp = np;
@@ -646,6 +689,7 @@ struct Lane : LaneEnv, LaneState {
         int i = next_int(n);   // nextInt(0) throws
         if (bad()) return;
         int cc = -1;
+        LN_NOUNROLL
         for (int t = 0; t < dm->N; t++) if (owner(t) == (int)ORX_OWNER_NONE && i-- == 0) { cc = t; break; }
         set_owner(cc, cp);
         set_pc(cp, pc(cp) + 1); set_ialp(cp, ialp(cp) - 1);
@@ -653,10 +697,11 @@ struct Lane : LaneEnv, LaneState {
         if (n - 1 == 0) { phase = ORX_PHASE_INITIAL_PLACEMENT; cp = 0; }   // tearDownCountrySelectionPhase
     }
     LN_M void setup_initial_placement_phase() { const int a = ialp(cp); placeable = a == 5 ? 5 : (a < 4 ? a : 4); }
-    LN_M void tear_down_initial_placement_phase()
+    LN_COLD void tear_down_initial_placement_phase()
     {
         const int P = dm->P;
         int np = cp + 1 == P ? 0 : cp + 1;
+        LN_NOUNROLL
         while (np != cp && ialp(np) == 0) np = np + 1 == P ? 0 : np + 1;
         if (np == cp) { cp = 0; phase = ORX_PHASE_CARDS; simTurn++; } else cp = np;
         playerTurns++;
@@ -668,12 +713,15 @@ struct Lane : LaneEnv, LaneState {
         uint32_t blo, bhi;
         border_mask(blo, bhi);
         int n = 0;
+        LN_NOUNROLL
         for (uint32_t m = blo; m; m &= m - 1u) { const int t = ln_ffs(m) - 1; if (armies(t) > 1) set_alist(n++, t); }
+        LN_NOUNROLL
         for (uint32_t m = bhi; m; m &= m - 1u) { const int t = 32 + ln_ffs(m) - 1; if (armies(t) > 1) set_alist(n++, t); }
         nAtt = n; selIters = 0;
     }
     LN_M void alist_remove(int i)
     {
+        LN_NOUNROLL
         for (int k = i; k < nAtt - 1; k++) set_alist(k, alist(k + 1));
         nAtt--;
     }
@@ -702,6 +750,7 @@ struct Lane : LaneEnv, LaneState {
         const int zero_ok = (h_phase == ORX_PHASE_ATTACK && h_astate == ORX_ATTACK_INVADE) ? h_dcc : -1;
 
         // setupCountries (:192-203)
+        LN_NOUNROLL
         for (int t = 0; t < N; t++) {
             const int o = LN_LDG(leaf + dm->off_owner + t);
             const int a = LN_LDG((const int32_t *)(leaf + dm->off_armies) + t);
@@ -709,11 +758,14 @@ struct Lane : LaneEnv, LaneState {
             if (a < (t == zero_ok ? 0 : 1) || a > ORX_MAX_ARMIES) bad_ = true;
             set_owner(t, o); set_armies(t, a);
         }
+        LN_NOUNROLL
         for (int li = 0; li <= P; li++) set_ncard(li, 0);
+        LN_NOUNROLL
         for (int p = 0; p < P; p++) { set_pot(p, 0); set_pc(p, 0); }
         // cards: the real hand, then the unseen deck (CardManager.simReset :240-248)
         if (!bad_) {
             const uint8_t *lc = leaf + dm->off_cards;
+            LN_NOUNROLL
             for (int i = 0; i < n_hand + n_deck; i++) {
                 const int c = LN_LDG(lc + i);
                 if (!(c < N || c == (int)ORX_CARD_WILD)) bad_ = true;
@@ -731,9 +783,11 @@ struct Lane : LaneEnv, LaneState {
         deal = ((uint64_t)(long long)h_deal_seed ^ 0x5DEECE66Dull) & ((1ull << 48) - 1ull);   // new Random(simDeck.hashCode())
 
         // setupCardState (:205-227): hidden hands, in player order
+        LN_NOUNROLL
         for (int p = 0; p < P; p++) {
             if (p == cp) continue;
             const int want = LN_LDG(leaf + dm->off_ncards + p);
+            LN_NOUNROLL
             for (int j = 0; j < want; j++) {
                 const int card = sim_deal();
                 if (card < 0) { fail(); return; }
@@ -742,6 +796,7 @@ struct Lane : LaneEnv, LaneState {
             }
         }
         // setupGeneralGameState (:229-276)
+        LN_NOUNROLL
         for (int t = 0; t < N; t++) { const int o = owner(t); if (o < P) set_pc(o, pc(o) + 1); }
         if (phase == ORX_PHASE_COUNTRY_SELECTION) remaining = P;
         else { remaining = 0; for (int p = 0; p < P; p++) remaining += pc(p) > 0; }
@@ -749,11 +804,14 @@ struct Lane : LaneEnv, LaneState {
         // setupPhaseGameState (:278-359)
         switch (phase) {
         case ORX_PHASE_COUNTRY_SELECTION:
+            LN_NOUNROLL
             for (int p = 0; p < P; p++) set_ialp(p, dm->start_armies + (p > 1 ? p : 0) - pc(p));
             break;
         case ORX_PHASE_INITIAL_PLACEMENT:
+            LN_NOUNROLL
             for (int p = 0; p < P; p++) {
                 int tot = 0;
+                LN_NOUNROLL
                 for (int t = 0; t < N; t++) if (owner(t) == p) tot += armies(t);
                 set_ialp(p, dm->start_armies + (p > 1 ? p : 0) - tot);
             }
@@ -870,6 +928,7 @@ struct Lane : LaneEnv, LaneState {
     // the phase loop of simulate (:435-479) up to the point where an attack phase has somebody to attack with
     LN_COLD void advance()
     {
+        LN_NOUNROLL
         for (;;) {
             if (bad() || remaining <= 1) { st = LS_NEW; return; }
             switch (phase) {
@@ -930,7 +989,6 @@ struct Lane : LaneEnv, LaneState {
     {
         // engine watchdog (the reference would spin forever): an attack phase cannot need this many trips on a valid board
         if (++selIters > LN_MAX_SEL_ITERS) { fail(); st = LS_TURN; return; }
-        topup();
         const int ai = next_int_small<false>(nAtt);
         const int A = alist(ai);
         const uint32_t elo = nbr_lo(A) & ~mine_lo, ehi = nbr_hi(A) & ~mine_hi;
@@ -944,6 +1002,7 @@ struct Lane : LaneEnv, LaneState {
         // the j-th non-owned out-neighbour in getAdjoiningList() order
         int D = -1;
         const int row = dm->adj_off + A * dm->degp, dg = (int)mapb(dm->deg_off + A);
+        LN_NOUNROLL
         for (int q = 0; q < dg; q++) {
             const int nb = (int)mapb(row + q);
             if (!is_mine(nb)) { if (j == 0) { D = nb; break; } j--; }
@@ -963,7 +1022,6 @@ struct Lane : LaneEnv, LaneState {
     // DICE: up to two single rolls (one Philox counter) of the "either side above 100" loop (O/BattleSim.java:99-116)
     LN_M void sec_dice()
     {
-        topup();
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
@@ -977,6 +1035,7 @@ struct Lane : LaneEnv, LaneState {
     // COOP on the host emulation: the rolls the warp would make together (3 v 2 dice only), one after the other
     LN_M void sec_coop_host()
     {
+        LN_NOUNROLL
         while ((ra > 100 || rd > 100) && ra >= 3 && rd >= 2) {
             const uint64_t k = next_k53<true>();
             const int x = single_roll(3, 2, k);
@@ -990,10 +1049,9 @@ struct Lane : LaneEnv, LaneState {
     // :797-841) and the list edits of SimRandom.attackPhase (SimRandom.java:121-137)
     LN_M void sec_fin()
     {
-        topup();
         if (ra > 0 && rd > 0) {
             int al, dl;
-            table_battle(ra, rd, next_k53<false>(), al, dl);
+            table_battle(ra, rd, next_k53<true>(), al, dl);
             ra -= al; rd -= dl;
         }
         const int A = bA, D = bD, me = cp;
@@ -1008,26 +1066,34 @@ struct Lane : LaneEnv, LaneState {
             const int available = aArm - 1;
             if (available == 0) { fail(); st = LS_TURN; return; }
             int inv = available;
-            if (available > 3) inv = 3 + next_int(available - 3);
+            if (available > 3) inv = 3 + next_int_hot(available - 3);
             aArm -= inv; dArm = inv;
-            set_armies(A, aArm); set_armies(D, dArm);
-            if (left == 0) player_defeated(dp, me);   // finishInvasion
             fl |= LF_INVADED;
-            if (aArm == 1) alist_remove(bai);
-            if (dArm > 1) { set_alist(nAtt, D); nAtt++; }
-        } else {
-            set_armies(A, aArm); set_armies(D, dArm);
-            if (aArm == 1) alist_remove(bai);   // ATTACKERS_DESTROYED
+            if (left == 0) { rd = dp; ra = aArm; bD |= dArm > 1 ? 0x100 : 0; st = LS_ELIM; }   // finishInvasion: the defender is out (rare: out of line)
         }
+        set_armies(A, aArm); set_armies(D, dArm);
+        if (st == LS_ELIM) return;
+        if (aArm == 1) alist_remove(bai);              // ATTACKERS_DESTROYED, or a conquest that left one army behind
+        if (rd == 0 && dArm > 1) { set_alist(nAtt, D); nAtt++; }
+        st = (nAtt == 0 || bad()) ? LS_TURN : LS_SEL;
+    }
+    // ELIM: playerDefeated for the conquest FIN has just booked, then the list edits FIN skipped
+    LN_COLD void sec_elim()
+    {
+        const int D = bD & 0xFF, dp = rd, aArm = ra;
+        player_defeated(dp, cp);
+        if (aArm == 1) alist_remove(bai);
+        if (bD & 0x100) { set_alist(nAtt, D); nAtt++; }
         st = (nAtt == 0 || bad()) ? LS_TURN : LS_SEL;
     }
 
     // ---- result record (SimulationBoard.java:1031-1044 + the parity pins of orx_state.h) ---------------------
-    LN_M void game_result(OrxGameResult &r) const
+    LN_COLD void game_result(OrxGameResult &r) const
     {
         uint32_t flags = fl & LF_ERRMASK;
         const bool dead = (flags & (ORX_FLAG_ERROR | ORX_FLAG_STREAM_END)) != 0u;
         if (dead) flags = (flags & ORX_FLAG_STREAM_END) ? ORX_FLAG_STREAM_END : ORX_FLAG_ERROR;
+        LN_NOUNROLL
         for (int p = 0; p < ORX_MAX_PLAYERS; p++) r.player_out_on_turn[p] = (!dead && p < dm->P) ? pot(p) : 0;
         r.sim_turn_count = dead ? 0 : simTurn;
         r.flags = flags;
@@ -1049,8 +1115,9 @@ struct Lane : LaneEnv, LaneState {
 #define ORX_LANE_MIN_BLOCKS 9
 #endif
 
-__device__ __forceinline__ void lane_write_result(const Lane &L, const LaneArgs &ar)
+__device__ __noinline__ void lane_write_result(const Lane *Lp, const LaneArgs *arp)
 {
+    const Lane &L = *Lp; const LaneArgs &ar = *arp;
     OrxGameResult r;
     L.game_result(r);
     if (ar.games) {
@@ -1061,6 +1128,7 @@ __device__ __forceinline__ void lane_write_result(const Lane &L, const LaneArgs 
     if (ar.agg) {
         unsigned long long *a = (unsigned long long *)(ar.agg + L.gidx / (unsigned long long)ar.playouts_per_leaf);
         atomicAdd(a + 0, 1ull); atomicAdd(a + 1, (unsigned long long)(long long)r.sim_turn_count);
+#pragma unroll 1
         for (int p = 0; p < ORX_MAX_PLAYERS; p++)
             if (r.player_out_on_turn[p] == -1) { atomicAdd(a + 2 + p, 1ull); atomicAdd(a + 10 + p, (unsigned long long)(long long)r.sim_turn_count); }
         if (r.flags) atomicAdd(a + 18, 1ull);
@@ -1080,45 +1148,44 @@ __device__ __forceinline__ void lane_coop_dice(const DevMap &dm, const LaneArgs 
     const int lane = lane_id();
     const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
     const uint32_t lt = lanemask_lt();
-    for (;;) {
+    bool more = true;
+#pragma unroll 1
+    while (more) {
         const uint32_t e = pos & 3u, c0 = pos >> 2;
         uint32_t o[4];
         ln_philox(c0 + (uint32_t)lane, g0, g1, ar.rk, o);
-        uint32_t a0, a1, b0, b1;
-        bool vB = true;
-        if (e & 1u) {   // doubles straddle the counters: (o1, o2) and (o3, next lane's o0)
-            const uint32_t n0 = __shfl_down_sync(ORX_FULL, o[0], 1);
-            a0 = o[1]; a1 = o[2]; b0 = o[3]; b1 = n0; vB = lane < 31;
-        } else { a0 = o[0]; a1 = o[1]; b0 = o[2]; b1 = o[3]; }
+        // doubles straddle the counters when pos is odd: (o1, o2) and (o3, next lane's o0)
+        const uint32_t n0 = __shfl_down_sync(ORX_FULL, o[0], 1);
+        const bool odd = (e & 1u) != 0u;
+        const uint32_t a0 = odd ? o[1] : o[0], a1 = odd ? o[2] : o[1], b0 = odd ? o[3] : o[2], b1 = odd ? n0 : o[3];
+        const bool vB = !(odd && lane == 31);
         const int rA = 2 * lane - (int)(e >> 1);      // index of this lane's first double among the block's rolls (-1: before pos)
         const bool vA = rA >= 0;
         const int nb = 64 - (int)(e & 1u) - (int)(e >> 1);
         const uint64_t kA = ((uint64_t)(a0 >> 6) << 27) + (uint64_t)(a1 >> 5), kB = ((uint64_t)(b0 >> 6) << 27) + (uint64_t)(b1 >> 5);
         const int xA = vA ? (int)(kA > t0) + (int)(kA > t1) : 0, xB = vB ? (int)(kB > t0) + (int)(kB > t1) : 0;
         const int hi = ra > rd ? ra : rd;
+        int la, played = nb;   // attacker losses and rolls consumed by this block
         if (ra - 2 * nb >= 3 && rd - 2 * nb >= 2 && (hi - 2 * nb > 100 || ra + rd - 2 * nb > 200)) {
-            const int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)(xA + xB));
-            ra -= la; rd -= 2 * nb - la; pos += 2u * (uint32_t)nb;
-            continue;
+            la = (int)__reduce_add_sync(ORX_FULL, (unsigned)(xA + xB));
+        } else {
+            const int sx = xA + xB;   // 0..4
+            const uint32_t m0 = __ballot_sync(ORX_FULL, sx & 1), m1 = __ballot_sync(ORX_FULL, sx & 2), m2 = __ballot_sync(ORX_FULL, sx & 4);
+            const int pre = __popc(m0 & lt) + 2 * __popc(m1 & lt) + 4 * __popc(m2 & lt);
+            const int cA = pre + xA, cB = cA + xB;                  // attacker losses up to and including this lane's doubles
+            const int raA = ra - cA, rdA = rd - (2 * (rA + 1) - cA), raB = ra - cB, rdB = rd - (2 * (rA + 2) - cB);
+            const bool goA = (raA > 100 || rdA > 100) && raA >= 3 && rdA >= 2, goB = (raB > 100 || rdB > 100) && raB >= 3 && rdB >= 2;
+            const uint32_t sA = __ballot_sync(ORX_FULL, vA && !goA), sB = __ballot_sync(ORX_FULL, vB && !goB);
+            la = __popc(m0) + 2 * __popc(m1) + 4 * __popc(m2);      // the block ends before the loop does
+            if (sA | sB) {
+                const int fa = sA ? __ffs(sA) - 1 : 32, fb = sB ? __ffs(sB) - 1 : 32;
+                const bool first = fa <= fb;                          // the stopping roll is lane fa's first / lane fb's second double
+                la = __shfl_sync(ORX_FULL, first ? cA : cB, first ? fa : fb);
+                played = (first ? 2 * fa + 1 : 2 * fb + 2) - (int)(e >> 1);
+                more = false;
+            }
         }
-        const int sx = xA + xB;   // 0..4
-        const uint32_t m0 = __ballot_sync(ORX_FULL, sx & 1), m1 = __ballot_sync(ORX_FULL, sx & 2), m2 = __ballot_sync(ORX_FULL, sx & 4);
-        const int pre = __popc(m0 & lt) + 2 * __popc(m1 & lt) + 4 * __popc(m2 & lt);
-        const int cA = pre + xA, cB = cA + xB;                  // attacker losses up to and including this lane's doubles
-        const int raA = ra - cA, rdA = rd - (2 * (rA + 1) - cA), raB = ra - cB, rdB = rd - (2 * (rA + 2) - cB);
-        const bool goA = (raA > 100 || rdA > 100) && raA >= 3 && rdA >= 2, goB = (raB > 100 || rdB > 100) && raB >= 3 && rdB >= 2;
-        const uint32_t sA = __ballot_sync(ORX_FULL, vA && !goA), sB = __ballot_sync(ORX_FULL, vB && !goB);
-        if ((sA | sB) == 0u) {   // the block ends before the loop does
-            const int la = __popc(m0) + 2 * __popc(m1) + 4 * __popc(m2);
-            ra -= la; rd -= 2 * nb - la; pos += 2u * (uint32_t)nb;
-            continue;
-        }
-        const int fa = sA ? __ffs(sA) - 1 : 32, fb = sB ? __ffs(sB) - 1 : 32;
-        int la, played;   // losses and rolls up to and including the stopping roll
-        if (fa <= fb) { la = __shfl_sync(ORX_FULL, cA, fa); played = 2 * fa - (int)(e >> 1) + 1; }
-        else { la = __shfl_sync(ORX_FULL, cB, fb); played = 2 * fb - (int)(e >> 1) + 2; }
         ra -= la; rd -= 2 * played - la; pos += 2u * (uint32_t)played;
-        return;
     }
 }
 
@@ -1154,7 +1221,7 @@ rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ 
     for (;;) {
         // how many lanes wait for each section: one REDUX over 6-bit fields (NEW, TURN, SEL, DICE, FIN), one ballot for the rare states
         const uint32_t cnt = __reduce_add_sync(ORX_FULL, L.st <= LS_FIN ? 1u << (6 * L.st) : 0u);
-        const uint32_t rare = __ballot_sync(ORX_FULL, L.st == LS_COOP || L.st == LS_GAUSS);
+        const uint32_t rare = __ballot_sync(ORX_FULL, L.st == LS_COOP || L.st == LS_GAUSS);   // (LS_ELIM never survives a trip)
         if ((cnt | rare) == 0u) break;   // every lane is LS_EXIT
         const int nN = (int)(cnt & 63u), nT = (int)((cnt >> 6) & 63u), nS = (int)((cnt >> 12) & 63u), nF = (int)((cnt >> 24) & 63u);
         bool ran = (cnt >> 18 & 63u) != 0u || rare != 0u;
@@ -1168,10 +1235,12 @@ rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ 
                 if (lane == leader) base = atomicAdd(ar.ticket, (unsigned long long)__popc(m));
                 base = __shfl_sync(ORX_FULL, base, leader);
                 if (L.st == LS_NEW) {
-                    if (L.fl & LF_HASGAME) lane_write_result(L, ar);
-                    L.fl = 0u;
                     const unsigned long long idx = base + (unsigned long long)__popc(m & lanemask_lt());
-                    if (idx < ar.total) LANE_COLD(start_game(idx)); else L.st = LS_EXIT;
+                    Lane t_; (LaneEnv &)t_ = (const LaneEnv &)L; (LaneState &)t_ = (const LaneState &)L;
+                    if (t_.fl & LF_HASGAME) lane_write_result(&t_, &ar);
+                    t_.fl = 0u;
+                    if (idx < ar.total) t_.start_game(idx); else t_.st = LS_EXIT;
+                    (LaneState &)L = (const LaneState &)t_;
                 }
             } else aN++;
         }
@@ -1179,11 +1248,16 @@ rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ 
             if (force || nT >= tn.thr_turn || aT >= tn.age_turn) { aT = 0; ran = true; if (L.st == LS_TURN) LANE_COLD(sec_turn()); }
             else aT++;
         }
+        // the one place the hot sections' stream words come from: at least 8 buffered for every lane about to run one
+        if (L.st >= LS_SEL && L.st <= LS_FIN) L.topup();
         if (nS) {
             if (force || nS >= tn.thr_sel || aS >= tn.age_sel) { aS = 0; ran = true; if (L.st == LS_SEL) L.sec_sel(); }
             else aS++;
         }
-        // COOP: long dice battles, one lane after the other, rolled by the whole warp
+        if (__any_sync(ORX_FULL, L.st == LS_GAUSS)) { ran = true; if (L.st == LS_GAUSS) LANE_COLD(sec_gauss()); }
+        if (__any_sync(ORX_FULL, L.st == LS_DICE)) { ran = true; if (L.st == LS_DICE) L.sec_dice(); }
+        // COOP: long dice battles, one lane after the other, rolled by the whole warp.  After DICE: a lane handed back to
+        // DICE has restarted its ring and must pass the next trip's top-up first (FIN checks its reads)
         for (uint32_t mc = __ballot_sync(ORX_FULL, L.st == LS_COOP); mc; mc &= mc - 1u) {
             const int src = __ffs(mc) - 1;
             int cra = __shfl_sync(ORX_FULL, L.ra, src), crd = __shfl_sync(ORX_FULL, L.rd, src);
@@ -1196,11 +1270,12 @@ rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ 
             }
             ran = true;
         }
-        if (__any_sync(ORX_FULL, L.st == LS_GAUSS)) { ran = true; if (L.st == LS_GAUSS) LANE_COLD(sec_gauss()); }
-        if (__any_sync(ORX_FULL, L.st == LS_DICE)) { ran = true; if (L.st == LS_DICE) L.sec_dice(); }
         if (nF) {
-            if (force || nF >= tn.thr_fin || aF >= tn.age_fin) { aF = 0; ran = true; if (L.st == LS_FIN) L.sec_fin(); }
-            else aF++;
+            if (force || nF >= tn.thr_fin || aF >= tn.age_fin) {
+                aF = 0; ran = true;
+                if (L.st == LS_FIN) L.sec_fin();
+                if (__any_sync(ORX_FULL, L.st == LS_ELIM)) { if (L.st == LS_ELIM) LANE_COLD(sec_elim()); }
+            } else aF++;
         }
         force = !ran;
     }

@@ -62,12 +62,15 @@ int lanes_emulate(const OrxMap *map, const OrxRules *rules, const uint8_t *leave
     while (live > 0) {
         for (auto &w : warps) {   // one trip of the kernel's loop per warp, round robin (the ticket order is the only coupling)
             if (w.done) continue;
-            bool ran = false;
+            // the counts the kernel takes at the top of a trip (one REDUX + one ballot)
+            const int nN0 = count(w, LS_NEW), nT0 = count(w, LS_TURN), nS0 = count(w, LS_SEL), nD0 = count(w, LS_DICE), nF0 = count(w, LS_FIN);
+            const int rare0 = count(w, LS_COOP) + count(w, LS_GAUSS);
+            bool ran = nD0 > 0 || rare0 > 0;
             int n;
-            if ((n = count(w, LS_NEW)) > 0) {
-                if (w.force || n >= tn.thr_new || w.aN >= tn.age_new) {
-                    w.aN = 0; ran = true; note(0, n);
-                    unsigned long long base = ticket; ticket += (unsigned long long)n;
+            if (nN0 > 0) {
+                if (w.force || nN0 >= tn.thr_new || w.aN >= tn.age_new) {
+                    w.aN = 0; ran = true; note(0, nN0);
+                    unsigned long long base = ticket; ticket += (unsigned long long)nN0;
                     int rank = 0;
                     for (int l = 0; l < 32; l++) {
                         Lane &L = w.L[l];
@@ -79,20 +82,25 @@ int lanes_emulate(const OrxMap *map, const OrxRules *rules, const uint8_t *leave
                     }
                 } else w.aN++;
             }
-            if ((n = count(w, LS_TURN)) > 0) {
-                if (w.force || n >= tn.thr_turn || w.aT >= tn.age_turn) { w.aT = 0; ran = true; note(1, n); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_TURN) w.L[l].sec_turn(); }
+            if (nT0 > 0) {
+                if (w.force || nT0 >= tn.thr_turn || w.aT >= tn.age_turn) { w.aT = 0; ran = true; note(1, count(w, LS_TURN)); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_TURN) w.L[l].sec_turn(); }
                 else w.aT++;
             }
-            if ((n = count(w, LS_SEL)) > 0) {
-                if (w.force || n >= tn.thr_sel || w.aS >= tn.age_sel) { w.aS = 0; ran = true; note(2, n); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_SEL) w.L[l].sec_sel(); }
+            for (int l = 0; l < 32; l++) if (w.L[l].st >= LS_SEL && w.L[l].st <= LS_FIN) w.L[l].topup();
+            if (nS0 > 0) {
+                if (w.force || nS0 >= tn.thr_sel || w.aS >= tn.age_sel) { w.aS = 0; ran = true; note(2, count(w, LS_SEL)); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_SEL) w.L[l].sec_sel(); }
                 else w.aS++;
             }
-            if (count(w, LS_COOP) > 0) { ran = true; if (stats) stats[5 * 34 + 1] += (unsigned long long)count(w, LS_COOP); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_COOP) w.L[l].sec_coop_host(); }
             if (count(w, LS_GAUSS) > 0) { ran = true; for (int l = 0; l < 32; l++) if (w.L[l].st == LS_GAUSS) w.L[l].sec_gauss(); }
             if ((n = count(w, LS_DICE)) > 0) { ran = true; note(3, n); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_DICE) w.L[l].sec_dice(); }
-            if ((n = count(w, LS_FIN)) > 0) {
-                if (w.force || n >= tn.thr_fin || w.aF >= tn.age_fin) { w.aF = 0; ran = true; note(4, n); for (int l = 0; l < 32; l++) if (w.L[l].st == LS_FIN) w.L[l].sec_fin(); }
-                else w.aF++;
+            // COOP after DICE: a lane the warp hands back to DICE has restarted its ring and waits for the next trip's top-up
+            if ((n = count(w, LS_COOP)) > 0) { ran = true; if (stats) stats[5 * 34 + 1] += (unsigned long long)n; for (int l = 0; l < 32; l++) if (w.L[l].st == LS_COOP) w.L[l].sec_coop_host(); }
+            if (nF0 > 0) {
+                if (w.force || nF0 >= tn.thr_fin || w.aF >= tn.age_fin) {
+                    w.aF = 0; ran = true; note(4, count(w, LS_FIN));
+                    for (int l = 0; l < 32; l++) if (w.L[l].st == LS_FIN) w.L[l].sec_fin();
+                    for (int l = 0; l < 32; l++) if (w.L[l].st == LS_ELIM) w.L[l].sec_elim();
+                } else w.aF++;
             }
             if (count(w, LS_EXIT) == 32) { w.done = true; live--; }
             w.force = !ran;
