@@ -12,14 +12,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
-LIB = os.path.join(HERE, "liborx.so")
+LIB = os.environ.get("ORX_BUILD_OUT") or os.path.join(HERE, "liborx.so")   # ORX_BUILD_OUT: variant builds
 SOURCES = [os.path.join(CSRC, "orx_api.cu"), os.path.join(CSRC, "orx_tree.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("orx_device.cuh", "orx_game.cuh")] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("orx_device.cuh", "orx_game.cuh", "orx_lanes.cuh", "orx_devmap.h", "orx_mapimage.h")] + \
     [os.path.join(INCLUDE, f) for f in ("orx.h", "orx_state.h", "orx_tree.h")] + [os.path.join(HERE, "ptx_uniform.py")]
 
-#: resident blocks per SM that ptxas budgets registers for (9 x 128 threads -> 56 registers).  The source carries a
-#: loose bound (ORX_MIN_BLOCKS 5) for the front end; see ptx_uniform.transform.
-PTXAS_MIN_BLOCKS = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS", "9"))
+#: resident blocks per SM that ptxas budgets registers for (11 x 128 threads -> 40 registers; round 2 sweep).  The source carries a
+#: loose bound (ORX_MIN_BLOCKS 4) for the front end; see ptx_uniform.transform.
+PTXAS_MIN_BLOCKS = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS", "11"))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]
@@ -32,11 +32,24 @@ def nvcc() -> str:
     return exe
 
 
+def source_hash() -> str:
+    """content hash of everything liborx.so is built from (sources, headers, the PTX pass, the build knobs)"""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(DEPS + [os.path.abspath(__file__)]):
+        h.update(os.path.basename(d).encode()); h.update(open(d, "rb").read())
+    for k in ("ORX_PTXAS_MIN_BLOCKS", "ORX_DEFINES", "ORX_PAD", "ORX_NVVM_MIN_BLOCKS"):
+        h.update(f"{k}={os.environ.get(k, '')};".encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    """the library is rebuilt when the hash of its sources differs from the one recorded at its last build (mtimes
+    are arbitrary after a checkout, and the prebuilt .so travels to the GPU box)"""
+    stamp = LIB + ".srchash"
+    if not os.path.exists(LIB) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return open(stamp).read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> str:
@@ -46,8 +59,11 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
     if not (force or is_stale()):
         return LIB
     flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-    if os.environ.get("ORX_PAD"):                   # tuning knob: code alignment of the rollout kernels
-        flags = flags + [f"-DORX_PAD={int(os.environ['ORX_PAD'])}"]
+    for d in os.environ.get("ORX_DEFINES", "").split():   # tuning knob: extra -D flags (variant builds, scripts/gpu_variants.sh)
+        flags = flags + ["-D" + d]
+    pad = int(os.environ.get("ORX_PAD", "2"))        # code alignment of the rollout kernels (fetch alignment: +-1 %)
+    if pad:
+        flags = flags + [f"-DORX_PAD={pad}"]
     if os.environ.get("ORX_NVVM_MIN_BLOCKS"):      # tuning knob: the loose bound the front end sees
         flags = flags + [f"-DORX_MIN_BLOCKS={int(os.environ['ORX_NVVM_MIN_BLOCKS'])}"]
     if not uniform:
@@ -57,9 +73,12 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
             sys.stderr.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        open(LIB + ".srchash", "w").write(source_hash())
         return LIB
-    keep = os.path.join(HERE, "build")
-    os.makedirs(keep, exist_ok=True)
+    # nvcc's intermediates (preprocessed CUDA headers, cudafe output) never live inside the tree: a scratch directory
+    # outside the repository, removed when the build ends
+    import tempfile
+    keep = tempfile.mkdtemp(prefix="orx_build_")
     cmd = [nvcc()] + flags + ["--dryrun", "--keep", "--keep-dir", keep, "-o", LIB] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.join(HERE, ".."))
     if r.returncode != 0:
@@ -83,8 +102,10 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
     r = subprocess.run(["bash", sh], capture_output=True, text=True, cwd=os.path.join(HERE, ".."))
     if verbose:
         sys.stderr.write(r.stderr)
+    shutil.rmtree(keep, ignore_errors=True)
     if r.returncode != 0:
         raise RuntimeError("liborx.so build failed:\n" + r.stdout + r.stderr)
+    open(LIB + ".srchash", "w").write(source_hash())
     return LIB
 
 

@@ -13,7 +13,7 @@
 
 #define ORX_BLOCK_THREADS 128
 #ifndef ORX_MIN_BLOCKS
-#define ORX_MIN_BLOCKS 5   /* bound seen by the front end; ptxas gets the tight one (build.py) */
+#define ORX_MIN_BLOCKS 4   /* bound seen by the front end; ptxas gets the tight one (build.py) */
 #endif
 
 #include "../../include/orx.h"
@@ -150,11 +150,14 @@ __global__ void battles_kernel(const __grid_constant__ DevMap dm, int a, int d, 
     Stream<false> s;
     s.init(to_saddr(sm[wid] + 8), to_saddr(sm[wid]), seed, first_game + (unsigned long long)i, nullptr, 0);
     int al = 0, dl = 0;
+    uint32_t rk[20];
+#pragma unroll
+    for (int r = 0; r < 10; r++) { rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u; rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u; }
     if (individual) {
         if (a < 1 || a > 3 || d < 1 || d > 2) s.flags |= ORX_FLAG_ERROR;
         else al = single_roll(dm, a, d, s.next_k53());
     } else if (a >= 1 && d >= 1) {
-        simulate_battle(dm, s, a, d, al, dl);
+        simulate_battle(dm, s, rk, a, d, al, dl);
     }
     if (lane_id() == 0) { al_out[i] = al; if (dl_out) dl_out[i] = dl; }
 }
@@ -497,6 +500,11 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStr
         return ORX_OK;
     }
     c->last_kernel = 1;
+    RolloutArgs wa = ar;
+    for (int r = 0; r < 10; r++) {
+        wa.rk[2 * r] = (uint32_t)ar.seed + (uint32_t)r * 0x9E3779B9u;
+        wa.rk[2 * r + 1] = (uint32_t)(ar.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     const RolloutKernel kern = kernel_for(c->nwt, replay, c->modelling);
     unsigned long long warps = (unsigned long long)c->sm_count * c->blocks_per_sm[(int)replay + 2 * (int)c->modelling] * (ORX_BLOCK_THREADS / 32);
     unsigned long long need = (ar.total + (ORX_BLOCK_THREADS / 32) - 1) / (ORX_BLOCK_THREADS / 32);
@@ -510,7 +518,7 @@ static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStr
     }
     if (timed) CK(cudaEventRecord(c->ev0, stream));
     dim3 grid((unsigned)blocks), block(ORX_BLOCK_THREADS);
-    kern<<<grid, block, c->smem_bytes, stream>>>(c->dm, ar);
+    kern<<<grid, block, c->smem_bytes, stream>>>(c->dm, wa);
     CK(cudaGetLastError());
     if (timed) { CK(cudaEventRecord(c->ev1, stream)); c->have_time = true; }
     c->launches++;

@@ -108,6 +108,15 @@ struct Stream {
         wi = 0u;
     }
 
+    // counter mode: continue at stream position p (>= pos()): inside the buffered block, or with the block that holds p
+    __device__ __forceinline__ void seek(uint32_t p)
+    {
+        if (p - base < 128u) { wi = p - base; return; }
+        base = p & ~127u;
+        philox_refill(buf, base >> 7, lds32(hdr + 4 * WH_G0), lds32(hdr + 4 * WH_G1), k0, k1);
+        wi = p & 127u;
+    }
+
     __device__ __forceinline__ uint32_t word()
     {
         if (REPLAY) {
@@ -257,6 +266,84 @@ __device__ __forceinline__ double next_gaussian(Stream<REPLAY> &s)
 // Java (int) cast of a double: truncate toward zero, saturate, NaN -> 0  (== cvt.rzi.s32.f64)
 __device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
 
+// Philox4x32-10 with the round keys precomputed on the host: rk[2r] = seed_lo + r * 0x9E3779B9, rk[2r+1] = seed_hi + r * 0xBB67AE85
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c2, uint32_t c3, const uint32_t *rk, uint32_t o[4])
+{
+    uint32_t c1 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+// The whole warp rolls one game's dice (both rollout kernels).  The "either side above 100" loop of BattleSim.simulateBattle
+// (O/BattleSim.java:99-116) while the dice stay 3 v 2: 32 lanes evaluate 32 consecutive Philox counters = 128 stream
+// words = up to 64 nextDouble()s, consumed in order from word `pos`; lane l holds the words 4 (c0 + l) .. + 3.  Two ways
+// through a block, both consuming exactly the doubles the reference's loop would:
+//   sum   no roll of the block can end the loop or change the dice: one REDUX over the attacker losses;
+//   scan  otherwise the first roll after which the loop stops (or a side drops below 3 v 2) is found from a warp prefix
+//         sum of the losses (three ballots) and two more ballots.
+// All arguments are warp-uniform; rk = the 20 Philox round keys (a kernel parameter: constant-bank operands).
+// Returns with ra, rd, pos advanced to just after the roll that ended the 3 v 2 regime.
+__device__ __forceinline__ void warp_dice_3v2(const DevMap &dm, const uint32_t *rk, int &ra, int &rd, uint32_t &pos, uint32_t g0, uint32_t g1)
+{
+    const int lane = lane_id();
+    const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
+    const uint32_t lt = lanemask_lt();
+    bool more = true;
+#pragma unroll 1
+    while (more) {
+        const uint32_t e = pos & 3u, c0 = pos >> 2;
+        uint32_t o[4];
+        philox4x32_10_rk(c0 + (uint32_t)lane, g0, g1, rk, o);
+        // doubles straddle the counters when pos is odd: (o1, o2) and (o3, next lane's o0)
+        const uint32_t n0 = __shfl_down_sync(ORX_FULL, o[0], 1);
+        const bool odd = (e & 1u) != 0u;
+        const uint32_t a0 = odd ? o[1] : o[0], a1 = odd ? o[2] : o[1], b0 = odd ? o[3] : o[2], b1 = odd ? n0 : o[3];
+        const bool vB = !(odd && lane == 31);
+        const int rA = 2 * lane - (int)(e >> 1);      // index of this lane's first double among the block's rolls (-1: before pos)
+        const bool vA = rA >= 0;
+        const int nb = 64 - (int)(e & 1u) - (int)(e >> 1);
+        const uint64_t kA = ((uint64_t)(a0 >> 6) << 27) + (uint64_t)(a1 >> 5), kB = ((uint64_t)(b0 >> 6) << 27) + (uint64_t)(b1 >> 5);
+#ifdef ORX_DICE_HI32
+        // compare the high 26 bits first: k > t  <=>  hi(k) > hi(t), unless they tie (2^-26 per compare: exact path then)
+        const uint32_t hA = a0 >> 6, hB = b0 >> 6, t0h = (uint32_t)(t0 >> 27), t1h = (uint32_t)(t1 >> 27);
+        int xA = (int)(hA > t0h) + (int)(hA > t1h), xB = (int)(hB > t0h) + (int)(hB > t1h);
+        if (__any_sync(ORX_FULL, hA == t0h || hA == t1h || hB == t0h || hB == t1h)) { xA = (int)(kA > t0) + (int)(kA > t1); xB = (int)(kB > t0) + (int)(kB > t1); }
+        if (!vA) xA = 0;
+        if (!vB) xB = 0;
+#else
+        const int xA = vA ? (int)(kA > t0) + (int)(kA > t1) : 0, xB = vB ? (int)(kB > t0) + (int)(kB > t1) : 0;
+#endif
+        const int hi = ra > rd ? ra : rd;
+        int la, played = nb;   // attacker losses and rolls consumed by this block
+        if (ra - 2 * nb >= 3 && rd - 2 * nb >= 2 && (hi - 2 * nb > 100 || ra + rd - 2 * nb > 200)) {
+            la = (int)__reduce_add_sync(ORX_FULL, (unsigned)(xA + xB));
+        } else {
+            const int sx = xA + xB;   // 0..4
+            const uint32_t m0 = __ballot_sync(ORX_FULL, sx & 1), m1 = __ballot_sync(ORX_FULL, sx & 2), m2 = __ballot_sync(ORX_FULL, sx & 4);
+            const int pre = __popc(m0 & lt) + 2 * __popc(m1 & lt) + 4 * __popc(m2 & lt);
+            const int cA = pre + xA, cB = cA + xB;                  // attacker losses up to and including this lane's doubles
+            const int raA = ra - cA, rdA = rd - (2 * (rA + 1) - cA), raB = ra - cB, rdB = rd - (2 * (rA + 2) - cB);
+            const bool goA = (raA > 100 || rdA > 100) && raA >= 3 && rdA >= 2, goB = (raB > 100 || rdB > 100) && raB >= 3 && rdB >= 2;
+            const uint32_t sA = __ballot_sync(ORX_FULL, vA && !goA), sB = __ballot_sync(ORX_FULL, vB && !goB);
+            la = __popc(m0) + 2 * __popc(m1) + 4 * __popc(m2);      // the block ends before the loop does
+            if (sA | sB) {
+                const int fa = sA ? __ffs(sA) - 1 : 32, fb = sB ? __ffs(sB) - 1 : 32;
+                const bool first = fa <= fb;                          // the stopping roll is lane fa's first / lane fb's second double
+                la = __shfl_sync(ORX_FULL, first ? cA : cB, first ? fa : fb);
+                played = (first ? 2 * fa + 1 : 2 * fb + 2) - (int)(e >> 1);
+                more = false;
+            }
+        }
+        ra -= la; rd -= 2 * played - la; pos += 2u * (uint32_t)played;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // BattleSim  (O/BattleSim.java)
 // ---------------------------------------------------------------------------------------
@@ -295,9 +382,11 @@ __device__ __forceinline__ int single_roll(const DevMap &dm, int pa, int pd, uin
     return k <= dm.single_thr[row][0] ? 0 : (k <= dm.single_thr[row][1] ? 1 : 2);
 }
 
-// BattleSim.simulateBattle (O/BattleSim.java:66-145)
-template <bool REPLAY>
-__device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY> &s, int attackers, int defenders,
+// BattleSim.simulateBattle (O/BattleSim.java:66-145); rk = Philox round keys of the launch (counter mode).
+// WARP_DICE = false keeps the single rolls one at a time (the once-per-game catch-up battle: the dice block is inlined
+// at one site only -- the kernel's instruction footprint matters, profiles/r2e).
+template <bool REPLAY, bool WARP_DICE = true>
+__device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY> &s, const uint32_t *rk, int attackers, int defenders,
                                                 int &alOut, int &dlOut)
 {
     int attackerLosses = 0, defenderLosses = 0;
@@ -316,6 +405,8 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
         }
     } else {
         int ra = attackers, rd = defenders;
+#ifndef ORX_DICE_REGS   // default: 64-roll / 32-roll steps over the doubles left in the shared-memory word block.  (ORX_DICE_REGS: the
+                       // register-resident block below, warp_dice_3v2 -- fewer instructions, measured slower in this kernel: DESIGN.md 8)
         // Single rolls while either side is above 100 (O/BattleSim.java:99-116).  Three ways through, all
         // consuming exactly the doubles the reference's loop would:
         //   scalar  one roll per trip when a side is about to run out (<= 2 armies), at a block boundary, or on replay;
@@ -372,6 +463,24 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
             const int x = single_roll(dm, pa, pd, s.next_k53());
             attackerLosses += x; defenderLosses += n - x; ra -= x; rd -= n - x;
         }
+#else
+        // Single rolls while either side is above 100 (O/BattleSim.java:99-116).  While the dice are 3 v 2 the whole warp
+        // rolls up to 64 of them per step straight from Philox counters in registers (warp_dice_3v2: exactly the doubles the
+        // reference's loop would draw); the few rolls with other dice (a side down to its last armies) and replayed streams
+        // go one at a time through the word buffer.
+        while ((ra > 100 || rd > 100) && ra > 0 && rd > 0 && !s.flags) {
+            if (!REPLAY && WARP_DICE && ra >= 3 && rd >= 2) {
+                uint32_t p = s.pos();
+                warp_dice_3v2(dm, rk, ra, rd, p, lds32(s.hdr + 4 * WH_G0), lds32(s.hdr + 4 * WH_G1));
+                s.seek(p);
+                continue;
+            }
+            const int pa = ra < 3 ? ra : 3, pd = rd < 2 ? rd : 2, n = pa < pd ? pa : pd;
+            const int x = single_roll(dm, pa, pd, s.next_k53());
+            ra -= x; rd -= n - x;
+        }
+#endif
+        attackerLosses = attackers - ra; defenderLosses = defenders - rd;
         if (ra != 0 && rd != 0 && !s.flags) {
             if (ra < 0 || rd < 0 || ra > ORX_TABLE_LIMIT || rd > ORX_TABLE_LIMIT) {
                 s.flags |= ORX_FLAG_ERROR;

@@ -26,6 +26,7 @@ struct RolloutArgs {
     unsigned long long *ticket;   // work counter (zeroed before launch)
     const uint32_t *words;        // replay: explicit streams
     uint32_t words_per_game;
+    uint32_t rk[20];              // Philox round keys of `seed`: rk[2r] = seed_lo + r * 0x9E3779B9, rk[2r+1] = seed_hi + r * 0xBB67AE85
 };
 
 template <int NWT, bool REPLAY, bool MODEL = false>
@@ -37,6 +38,7 @@ struct Game {
     saddr a_move;             // MODEL: Country.moveableArmies, int32 per territory
     uint32_t agents;          // MODEL: ORX_AGENT_* of player p in bits 3p..3p+2 (simAgents[], ModellingBoard.java)
     Stream<REPLAY> s;
+    const uint32_t *rk;       // RolloutArgs::rk (constant bank)
     int lane;
 
     // warp-uniform scalars (SimulationBoard.java:62-96)
@@ -326,7 +328,11 @@ struct Game {
     {
         int a = armies(A) - 1, d = armies(D);
         if (attackUntilDead) {
-            simulate_battle(dm, s, a, d, al, dl);
+#ifdef ORX_DICE_2SITE
+            simulate_battle<REPLAY, true>(dm, s, rk, a, d, al, dl);
+#else
+            simulate_battle<REPLAY, false>(dm, s, rk, a, d, al, dl);   // the catch-up battle of an EXECUTE leaf: once per game
+#endif
         } else {
             int pa = a < 3 ? a : 3, pd = d < 2 ? d : 2;
             if (pa < 1 || pd < 1) { fail(); al = dl = 0; return; }
@@ -458,7 +464,7 @@ struct Game {
             saddr pA = a_arm + 4u * (uint32_t)A, pD = a_arm + 4u * (uint32_t)D;
             int aArm = (int)lds32(pA), dArm = (int)lds32(pD);
             int al, dl;
-            simulate_battle(dm, s, aArm - 1, dArm, al, dl);
+            simulate_battle(dm, s, rk, aArm - 1, dArm, al, dl);
             aArm -= al; dArm -= dl;
             if (dArm == 0) {
                 // setupInvasion (:797-812)
@@ -607,7 +613,7 @@ struct Game {
     {
         attackUntilDead = 1;
         int aArm = armies(A), dArm = armies(D), al, dl;
-        simulate_battle(dm, s, aArm - 1, dArm, al, dl);
+        simulate_battle(dm, s, rk, aArm - 1, dArm, al, dl);
         if (s.flags) return 0;
         aArm -= al; dArm -= dl;
         __syncwarp();
@@ -1171,6 +1177,7 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
     g.s_adj = sbase + (uint32_t)dm.adj_off; g.s_deg = sbase + (uint32_t)dm.deg_off; g.s_sym = sbase + (uint32_t)dm.sym_off;
     g.s_nbr = sbase + (uint32_t)dm.nbr_off; g.s_cont = sbase + (uint32_t)dm.cont_off; g.s_bonus = sbase + (uint32_t)dm.bonus_off;
     g.lane = lane_id();
+    g.rk = ar.rk;
     g.a_hdr = wbase;
     g.a_arm = wbase + (uint32_t)dm.w_armies; g.a_own = wbase + (uint32_t)dm.w_owner;
     g.a_alist = wbase + (uint32_t)dm.w_alist; g.a_cards = wbase + (uint32_t)dm.w_cards;

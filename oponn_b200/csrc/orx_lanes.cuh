@@ -1135,60 +1135,6 @@ __device__ __noinline__ void lane_write_result(const Lane *Lp, const LaneArgs *a
     }
 }
 
-// COOP: the whole warp rolls one lane's dice.  The "either side above 100" loop of BattleSim.simulateBattle
-// (O/BattleSim.java:99-116) while the dice stay 3 v 2: 32 lanes evaluate 32 consecutive Philox counters = 128 stream
-// words = up to 64 nextDouble()s, consumed in order from word `pos`; lane l holds the words 4 (c0 + l) .. + 3.  Two ways
-// through a block, both consuming exactly the doubles the reference's loop would:
-//   sum   no roll of the block can end the loop or change the dice: one REDUX over the attacker losses;
-//   scan  otherwise the first roll after which the loop stops (or a side drops below 3 v 2) is found from a warp prefix
-//         sum of the losses (three ballots) and two more ballots.
-// All arguments are warp-uniform.  Returns with ra, rd, pos advanced; the caller decides DICE (dice changed) or FIN.
-__device__ __forceinline__ void lane_coop_dice(const DevMap &dm, const LaneArgs &ar, int &ra, int &rd, uint32_t &pos, uint32_t g0, uint32_t g1)
-{
-    const int lane = lane_id();
-    const uint64_t t0 = dm.single_thr[5][0], t1 = dm.single_thr[5][1];
-    const uint32_t lt = lanemask_lt();
-    bool more = true;
-#pragma unroll 1
-    while (more) {
-        const uint32_t e = pos & 3u, c0 = pos >> 2;
-        uint32_t o[4];
-        ln_philox(c0 + (uint32_t)lane, g0, g1, ar.rk, o);
-        // doubles straddle the counters when pos is odd: (o1, o2) and (o3, next lane's o0)
-        const uint32_t n0 = __shfl_down_sync(ORX_FULL, o[0], 1);
-        const bool odd = (e & 1u) != 0u;
-        const uint32_t a0 = odd ? o[1] : o[0], a1 = odd ? o[2] : o[1], b0 = odd ? o[3] : o[2], b1 = odd ? n0 : o[3];
-        const bool vB = !(odd && lane == 31);
-        const int rA = 2 * lane - (int)(e >> 1);      // index of this lane's first double among the block's rolls (-1: before pos)
-        const bool vA = rA >= 0;
-        const int nb = 64 - (int)(e & 1u) - (int)(e >> 1);
-        const uint64_t kA = ((uint64_t)(a0 >> 6) << 27) + (uint64_t)(a1 >> 5), kB = ((uint64_t)(b0 >> 6) << 27) + (uint64_t)(b1 >> 5);
-        const int xA = vA ? (int)(kA > t0) + (int)(kA > t1) : 0, xB = vB ? (int)(kB > t0) + (int)(kB > t1) : 0;
-        const int hi = ra > rd ? ra : rd;
-        int la, played = nb;   // attacker losses and rolls consumed by this block
-        if (ra - 2 * nb >= 3 && rd - 2 * nb >= 2 && (hi - 2 * nb > 100 || ra + rd - 2 * nb > 200)) {
-            la = (int)__reduce_add_sync(ORX_FULL, (unsigned)(xA + xB));
-        } else {
-            const int sx = xA + xB;   // 0..4
-            const uint32_t m0 = __ballot_sync(ORX_FULL, sx & 1), m1 = __ballot_sync(ORX_FULL, sx & 2), m2 = __ballot_sync(ORX_FULL, sx & 4);
-            const int pre = __popc(m0 & lt) + 2 * __popc(m1 & lt) + 4 * __popc(m2 & lt);
-            const int cA = pre + xA, cB = cA + xB;                  // attacker losses up to and including this lane's doubles
-            const int raA = ra - cA, rdA = rd - (2 * (rA + 1) - cA), raB = ra - cB, rdB = rd - (2 * (rA + 2) - cB);
-            const bool goA = (raA > 100 || rdA > 100) && raA >= 3 && rdA >= 2, goB = (raB > 100 || rdB > 100) && raB >= 3 && rdB >= 2;
-            const uint32_t sA = __ballot_sync(ORX_FULL, vA && !goA), sB = __ballot_sync(ORX_FULL, vB && !goB);
-            la = __popc(m0) + 2 * __popc(m1) + 4 * __popc(m2);      // the block ends before the loop does
-            if (sA | sB) {
-                const int fa = sA ? __ffs(sA) - 1 : 32, fb = sB ? __ffs(sB) - 1 : 32;
-                const bool first = fa <= fb;                          // the stopping roll is lane fa's first / lane fb's second double
-                la = __shfl_sync(ORX_FULL, first ? cA : cB, first ? fa : fb);
-                played = (first ? 2 * fa + 1 : 2 * fb + 2) - (int)(e >> 1);
-                more = false;
-            }
-        }
-        ra -= la; rd -= 2 * played - la; pos += 2u * (uint32_t)played;
-    }
-}
-
 __global__ void __launch_bounds__(ORX_LANE_THREADS, ORX_LANE_MIN_BLOCKS)
 rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ LaneArgs ar)
 {
@@ -1263,7 +1209,7 @@ rollout_lanes_kernel(const __grid_constant__ DevMap dm, const __grid_constant__ 
             int cra = __shfl_sync(ORX_FULL, L.ra, src), crd = __shfl_sync(ORX_FULL, L.rd, src);
             uint32_t cpos = __shfl_sync(ORX_FULL, L.pos, src);
             const uint32_t cg0 = __shfl_sync(ORX_FULL, L.g0, src), cg1 = __shfl_sync(ORX_FULL, L.g1, src);
-            lane_coop_dice(dm, ar, cra, crd, cpos, cg0, cg1);
+            warp_dice_3v2(dm, ar.rk, cra, crd, cpos, cg0, cg1);
             if (lane == src) {
                 L.ra = cra; L.rd = crd; L.pos = cpos; L.lim = cpos & ~3u;   // the ring restarts at the counter that holds pos
                 L.st = ((cra > 100 || crd > 100) && cra > 0 && crd > 0) ? LS_DICE : LS_FIN;
