@@ -8,6 +8,12 @@ random playouts from the frozen mid-game leaf ``classic42_mid_s1`` on each GPU (
 for N > 1, by the one exchange the path has: an NCCL all-reduce of the per-leaf win/length sums
 (root-parallel merge, once per move).  One JSON line on stdout; see DESIGN.md "Measurement".
 
+After the timed regions the same process runs BASELINE.json's other GPU configurations once each, short, and adds
+them to the line as ``extra_configs`` (not part of ``value``): config 3 in its full form (one independent search tree
+per GPU, root children merged by ONE all-reduce per move), config 4 (the 200-territory map, with its own roofline
+figures and shared-memory / occupancy numbers), config 5 (4,096 leaf states sharded over the GPUs, no collective).
+``--no-extra`` skips them.
+
 ``--impl reference`` times the CPU restatement of the Java simulator (oracle/, all host threads) on a
 bounded sample of the same workload: the Java reference itself cannot run here (no JDK, no Lux SDK).
 """
@@ -28,9 +34,17 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 RUN_SEED = 20261019
+CPU_PLAYOUTS_PER_THREAD = 512   # both CPU legs (cpu_baseline and --impl reference) use the same sample per thread
 METRIC = "risk_playouts_per_sec_to_terminal"
 UNIT = "playouts/s"
 WORKLOAD = "classic42 (42 territories, 6 players, cards on, transfer on), leaf classic42_mid_s1, all-SimRandom playouts"
+
+
+def bench_config(playouts: int, world: int) -> dict:
+    """the `config` object of both arms (ours and --impl reference): the workload the metric is quoted on"""
+    return {"workload": WORKLOAD, "playouts_per_gpu_per_step": playouts, "run_seed": RUN_SEED,
+            "l2": "256 MiB memset between steps (inputs are 304 B; the kernel is issue-bound, not memory-bound)",
+            "exchange": "none" if world == 1 else "NCCL all-reduce of 20 int64 per-leaf sums, once per step"}
 
 
 def load_leaf() -> np.ndarray:
@@ -41,24 +55,18 @@ def load_workload() -> dict:
     return json.load(open(os.path.join(ROOT, "tests", "golden", "workload_classic42_mid_s1.json")))
 
 
-def load_traffic(playouts: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch, from the committed ncu capture of the same
-    launch size (profiles/rollout_traffic.json); None when the capture was taken at another size."""
+def load_static_capture(playouts: int, kernel_kind: str) -> dict:
+    """Counters that bench.py cannot measure live (they need ncu): DRAM traffic, executed warp instructions and issue-slot
+    utilisation of ONE full-size rollout launch, from the committed capture profiles/rollout_traffic.json.  They are
+    constants of that capture, not of this run, and the line says so ("static_capture").  Empty when the capture was
+    taken at another launch size or for the other kernel."""
     p = os.path.join(ROOT, "profiles", "rollout_traffic.json")
     if not os.path.exists(p):
-        return None
+        return {}
     d = json.load(open(p))
-    return d["traffic_bytes_per_launch"] if d.get("playouts_per_launch") == playouts else None
-
-
-def load_issue_active(playouts: int):
-    """smsp__issue_active.avg.pct_of_peak_sustained_active / 100 of the same launch size, from the committed ncu capture
-    (the layout-aware companion of roofline.frac: how full the issue slots actually are)."""
-    p = os.path.join(ROOT, "profiles", "rollout_traffic.json")
-    if not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    return d["issue_active_pct"] / 100.0 if d.get("playouts_per_launch") == playouts else None
+    if d.get("playouts_per_launch") != playouts or d.get("kernel_kind", "warp") != kernel_kind:
+        return {}
+    return d
 
 
 def measured_peaks() -> dict:
@@ -137,14 +145,16 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = 64 * cores  # playouts per step: a bounded sample of the 1M-playout move
+    # playouts per step: a bounded sample of the 1M-playout move; 512 per thread so that the 12x spread of game lengths
+    # averages out inside a step (64 per thread under-reported the CPU by 22 %: VERDICT r1)
+    sample = CPU_PLAYOUTS_PER_THREAD * cores
     dt = cpu_rollouts(sample, cores, steps=args.steps, warmup=args.warmup)
     value = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "playouts_per_step": sample, "note": "bounded sample of the 1,048,576-playout move"},
+        "config": bench_config(args.playouts, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} playouts/step x {args.steps} steps, oracle/oponn_oracle.c -O2, {cores} threads "
                                    "(C restatement of the Java simulator; JVM and Lux SDK unavailable)"},
@@ -157,6 +167,120 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU side
 # ---------------------------------------------------------------------------------------------
+KERNEL_NAMES = {"warp": "orx::rollout_kernel<2,false,false> (one warp per game)", "lanes": "orx::rollout_lanes_kernel (one lane per game)",
+                "none": "none"}
+
+
+def run_extra_configs(world: int, rank: int, local: int, dev, args) -> dict:
+    """BASELINE.json configs 3, 4, 5, once each, short, outside the headline's timed regions.  Device times are CUDA
+    events on the library's stream (orx_last_kernel_ms) or wall clock bracketed by synchronize + barrier, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from oponn_b200.engine import RolloutEngine
+    from oponn_b200.maps import classic42, synth200
+    from oponn_b200.state import ATTACK_START, LEAF_RESULT_DTYPE, PHASE_ATTACK, BoardState, Rules
+    from oponn_b200.tree import SearchTree, TreeOptions, merge_root_children, move_str
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    out = {}
+    peaks = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    peak = sm_count * 4 * 32 * peaks["sm_max_mhz"] * 1e6 / 1e9
+    golden = os.path.join(ROOT, "tests", "golden")
+
+    # ---- config 3, full form: one independent tree per GPU, ONE all-reduce of the root children per move -------------
+    m = classic42(6)
+    eng = RolloutEngine(m, Rules(), device=local)
+    bs = BoardState.unpack(m, load_leaf())
+    bs.currentPhase, bs.attackState = PHASE_ATTACK, ATTACK_START
+    for t in range(m.n_territories):
+        if bs.owner[t] == 0:
+            bs.armies[t] = 6
+    ppl, lif, iters = 8, 16384, 163840          # 163,840 leaves x 8 playouts = 1,310,720 playouts per GPU per move
+    tree = SearchTree(m, Rules(), TreeOptions(agent_id=0, playouts_per_leaf=ppl, leaves_in_flight=lif, seed=1000 + rank), eng)
+    tree.search(bs, 2048)                        # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    ch, _ = tree.search(bs, iters)
+    merged = merge_root_children(ch, dev)        # the one exchange of the move
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    best = tree.choose(merged)
+    total = int(merged["visits"].sum())
+    out["config3_root_parallel"] = {
+        "what": "one independent UCT tree per GPU (virtual loss, 16,384 leaves in flight, 8 playouts per leaf), root children merged with ONE "
+                "all-reduce per move, then chooseRobustMove",
+        "n_gpus": world, "playouts_per_move": total, "seconds_per_move": dt, "playouts_per_s": total / dt,
+        "root_children": int(len(merged)), "best_move": move_str(merged[best]["move"]),
+        "agent_win_rate": float(merged["wins"][:, 0].sum() / max(total, 1)),
+        "note": "10,485,760 playouts per move at 8 GPUs; the per-GPU share (1,310,720) is fixed, so smaller N search fewer playouts per move"}
+    tree.close()
+    eng.close()
+
+    # ---- config 4: the 200-territory map ------------------------------------------------------------------------
+    m4, r4 = synth200(), Rules(max_player_turns=4096)
+    eng = RolloutEngine(m4, r4, device=local)
+    leaf4 = np.fromfile(os.path.join(golden, "synth200_mid_s1.leaf"), dtype=np.uint8)
+    ld = torch.from_numpy(leaf4.copy()).to(dev)
+    agg = torch.zeros(LEAF_RESULT_DTYPE.itemsize // 8, dtype=torch.int64, device=dev)
+    P4 = 65536
+    ms = []
+    for k in range(2):                           # first launch warms up
+        eng.rollout_batch_device(ld.data_ptr(), 1, P4, RUN_SEED, (k * world + rank) * P4, agg.data_ptr())
+        eng.sync()
+        ms.append(eng.last_kernel_ms)
+    k4 = max_over_ranks(ms[-1])
+    wl4 = json.load(open(os.path.join(golden, "workload_synth200_mid_s1.json")))
+    A4 = wl4["algorithmic_int_ops_per_playout"]
+    a = agg.cpu().numpy().view(LEAF_RESULT_DTYPE)
+    info = eng.kernel_info(P4)
+    out["config4_synth200"] = {
+        "what": "synth200 (200 territories, 10 continents, 8 players), leaf synth200_mid_s1, step cap 4,096 player-turns",
+        "n_gpus": world, "playouts_per_gpu": P4, "kernel_ms": k4, "playouts_per_s": P4 * world / (k4 * 1e-3),
+        "kernel": "orx::rollout_kernel<8,false,false> (one warp per game)", "launch": info,
+        "leaf_record_bytes": int(eng.layout.stride),
+        "roofline": {"bound": "int_issue", "achieved": A4 * P4 / (k4 * 1e-3) / 1e9, "peak": peak, "unit": "Gop/s",
+                     "frac": A4 * P4 / (k4 * 1e-3) / 1e9 / peak, "algorithmic_int_ops_per_playout": A4},
+        "mean_rounds": float(a["len_sum"][0] / max(int(a["n"][0]), 1)), "hit_step_cap": int(a["flagged"][0])}
+    eng.close()
+
+    # ---- config 5: 4,096 leaf states x 1,024 playouts, states sharded over the GPUs, no collective -----------------
+    eng = RolloutEngine(m, Rules(), device=local)
+    l64 = np.fromfile(os.path.join(golden, "classic42_mid_64.leaves"), dtype=np.uint8).reshape(64, -1)
+    n_states, ppl5 = 4096, 1024
+    lo, hi = n_states * rank // world, n_states * (rank + 1) // world
+    mine = np.ascontiguousarray(np.tile(l64, (n_states // 64, 1))[lo:hi])
+    ld = torch.from_numpy(mine).to(dev)
+    agg = torch.zeros((hi - lo) * (LEAF_RESULT_DTYPE.itemsize // 8), dtype=torch.int64, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    eng.rollout_batch_device(ld.data_ptr(), hi - lo, ppl5, RUN_SEED, lo * ppl5, agg.data_ptr())
+    eng.sync()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    a = agg.cpu().numpy().view(LEAF_RESULT_DTYPE)
+    ok = bool((a["n"] == ppl5).all())
+    out["config5_state_parallel"] = {
+        "what": "4,096 leaf states (the 64 committed mid-game leaves, 64 copies each with its own game-id range) x 1,024 playouts per "
+                "state, states partitioned over the GPUs, no collective; BASELINE.json asks 16,384 playouts per state: this is a "
+                "1/16 slice per state, same per-playout work",
+        "n_gpus": world, "states": n_states, "playouts_per_state": ppl5, "seconds": dt,
+        "playouts_per_s": n_states * ppl5 / dt, "kernel": KERNEL_NAMES[eng.last_kernel_kind], "every_state_complete": ok}
+    eng.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +371,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ksum = float(t.item())
     checks = agg_dev.cpu().numpy()
+    kernel_kind = eng.last_kernel_kind
     dt_e2e = timed(step_e2e, args.steps, min(args.warmup, 1), 1000)
 
     total_playouts = P * world * args.steps
@@ -257,6 +382,7 @@ def run_ours(args):
     if rank == 0:
         wl = load_workload()
         peaks = measured_peaks()
+        static = load_static_capture(P, kernel_kind)
         prop = torch.cuda.get_device_properties(local)
         sm_count = prop.multi_processor_count
         A = wl["algorithmic_int_ops_per_playout"]
@@ -268,20 +394,20 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "playouts_per_gpu_per_step": P, "run_seed": RUN_SEED,
-                       "l2": "256 MiB memset between steps (inputs are 304 B; the kernel is issue-bound, not memory-bound)",
-                       "exchange": "none" if world == 1 else "NCCL all-reduce of 20 int64 per-leaf sums, once per step"},
+            "config": bench_config(P, world),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": stride * world,
                     "d2h_bytes_per_step": LEAF_RESULT_DTYPE.itemsize * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "int_issue", "kernel": "orx::rollout_kernel<2,false,false>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "int_issue", "kernel": KERNEL_NAMES[kernel_kind], "achieved": achieved, "peak": peak,
                          "unit": "Gop/s", "frac": achieved / peak,
                          "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']} MHz "
                                         f"({peaks['_source']} clock, MEASURED_PEAKS.json)",
                          "algorithmic_int_ops_per_playout": A, "kernel_ms_avg": k_avg_ms,
-                         "traffic": load_traffic(P),
-                         "issue_slots_busy_ncu": load_issue_active(P),
+                         "traffic": static.get("traffic_bytes_per_launch"),
+                         "issue_slots_busy_ncu": (static["issue_active_pct"] / 100.0) if static else None,
+                         "warp_instructions_per_playout_ncu": (static["smsp_inst_executed"] / P) if static else None,
+                         "static_capture": static.get("source", "none for this launch size / kernel"),
                          "hbm_side_check": {"algorithmic_bytes_per_launch": alg_bytes,
                                             "achieved_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9,
                                             "peak_gbs": peaks["hbm_gbs"]}},
@@ -289,13 +415,18 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            sample = 128 * cores
+            sample = CPU_PLAYOUTS_PER_THREAD * cores
             cdt = cpu_rollouts(sample, cores)
             line["cpu_baseline"] = {"value": sample / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} playouts of the same leaf, oracle/oponn_oracle.c -O2, {cores} threads "
                                               "(C restatement of the Java simulator; JVM and Lux SDK unavailable)"}
-        print(json.dumps(line))
     eng.close()
+    if not args.no_extra:
+        extra = run_extra_configs(world, rank, local, dev, args)
+        if rank == 0:
+            line["extra_configs"] = extra
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -310,6 +441,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--playouts", type=int, default=1 << 20, help="playouts per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (BASELINE.json configs 3, 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

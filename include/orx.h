@@ -100,10 +100,16 @@ float    orx_last_kernel_ms(OrxCtx *ctx);
 uint64_t orx_kernel_launches(const OrxCtx *ctx);
 
 /* Which rollout kernel the last launch of this context used: 1 = warp-per-game (orx_game.cuh: any map, replay
- * streams, modelled opponents, small batches), 2 = lane-per-game (orx_lanes.cuh: all-SimRandom counter-stream batches
- * of at least ~4 games per resident lane on maps up to 64 territories), 0 = none yet.  Both produce identical
- * records; the environment variable ORX_KERNEL=warp|lanes overrides the choice (tests, profiling). */
+ * streams, modelled opponents: the default everywhere), 2 = lane-per-game (orx_lanes.cuh: all-SimRandom counter-stream
+ * batches on maps up to 64 territories; opt-in through the environment, ORX_KERNEL=lanes or ORX_LANE_MIN_TOTAL=n, because
+ * it is currently the slower of the two on B200), 0 = none yet.  Both produce identical records. */
 int orx_last_kernel_kind(const OrxCtx *ctx);
+
+/* Launch shape of the rollout kernel a counter-stream batch of `total_playouts` would run on with the context's current
+ * map and line-up: kind as above, resident blocks per SM, threads per block, dynamic shared memory per block (the
+ * board-in-shared-memory footprint BASELINE.json config 4 asks about).  Any output pointer may be NULL. */
+int orx_kernel_info(const OrxCtx *ctx, uint64_t total_playouts, int32_t *kind, int32_t *blocks_per_sm,
+                    int32_t *threads_per_block, int32_t *smem_bytes_per_block);
 
 /* Replaces: BattleSim.getAttackOutcomes(a, d) (BattleSim.java:174-184) for 1 <= a,d <= 100.
  * Rows are in the reference's order (descending probability, stable).  Returns the row count

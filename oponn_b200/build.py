@@ -21,6 +21,9 @@ DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("orx_device.cuh", "orx_game.cu
 #: loose bound (ORX_MIN_BLOCKS 4) for the front end; see ptx_uniform.transform.
 PTXAS_MIN_BLOCKS = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS", "11"))
 
+#: the same for the other instantiations (replay, modelled opponents, maps above 64 territories)
+PTXAS_MIN_BLOCKS_OTHER = int(os.environ.get("ORX_PTXAS_MIN_BLOCKS_OTHER", "9"))
+
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]
 
@@ -38,7 +41,7 @@ def source_hash() -> str:
     h = hashlib.sha256()
     for d in sorted(DEPS + [os.path.abspath(__file__)]):
         h.update(os.path.basename(d).encode()); h.update(open(d, "rb").read())
-    for k in ("ORX_PTXAS_MIN_BLOCKS", "ORX_DEFINES", "ORX_PAD", "ORX_NVVM_MIN_BLOCKS"):
+    for k in ("ORX_PTXAS_MIN_BLOCKS", "ORX_PTXAS_MIN_BLOCKS_OTHER", "ORX_DEFINES", "ORX_PAD", "ORX_NVVM_MIN_BLOCKS"):
         h.update(f"{k}={os.environ.get(k, '')};".encode())
     return h.hexdigest()
 
@@ -96,7 +99,7 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
         script.append(st)
         if "/cicc" in st.split(" ")[0] or st.lstrip().startswith('"$CICC_PATH/cicc"'):
             ptx = st.rsplit('-o "', 1)[1].rstrip('" ')
-            script.append(f'"{sys.executable}" "{os.path.join(HERE, "ptx_uniform.py")}" "{ptx}" "{ptx}" {PTXAS_MIN_BLOCKS}')
+            script.append(f'"{sys.executable}" "{os.path.join(HERE, "ptx_uniform.py")}" "{ptx}" "{ptx}" {PTXAS_MIN_BLOCKS} {PTXAS_MIN_BLOCKS_OTHER} "{LIB}.ptxpass.json"')
     sh = os.path.join(keep, "build.sh")
     open(sh, "w").write("\n".join(script) + "\n")
     r = subprocess.run(["bash", sh], capture_output=True, text=True, cwd=os.path.join(HERE, ".."))
@@ -107,6 +110,25 @@ def build(force: bool = False, verbose: bool = False, uniform: bool = True) -> s
         raise RuntimeError("liborx.so build failed:\n" + r.stdout + r.stderr)
     open(LIB + ".srchash", "w").write(source_hash())
     return LIB
+
+
+#: the same sources compiled WITHOUT the PTX pass: the check library of tests/test_gpu_ptx_guard.py (never loaded by the product)
+LIB_NOUNIFORM = os.path.join(HERE, "liborx_nouniform.so")
+
+
+def build_nouniform(force: bool = False) -> str:
+    """plain nvcc build (no bra.uni rewriting, source launch bounds): its records must equal the shipped library's"""
+    global LIB
+    stamp = LIB_NOUNIFORM + ".srchash"
+    if not force and os.path.exists(LIB_NOUNIFORM) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash():
+        return LIB_NOUNIFORM
+    keep = LIB
+    try:
+        LIB = LIB_NOUNIFORM
+        build(force=True, uniform=False)
+    finally:
+        LIB = keep
+    return LIB_NOUNIFORM
 
 
 if __name__ == "__main__":

@@ -313,8 +313,11 @@ static int configure_lanes(OrxCtx *c)
         int32_t *dst[9] = { &t.thr_new, &t.thr_turn, &t.thr_sel, &t.thr_fin, &t.age_new, &t.age_turn, &t.age_sel, &t.age_fin, &t.coop_min };
         for (int i = 0; i < n && i < 9; i++) *dst[i] = v[i];
     }
-    // auto: at least 4 games per resident lane, so that the tail of a launch (lanes running dry) stays small
-    c->lane_min_total = 4ull * (unsigned long long)c->sm_count * (unsigned long long)c->lane_blocks_per_sm * ORX_LANE_THREADS;
+    // The lane kernel is opt-in: measured on B200 it executes 30 % fewer warp instructions per playout than the
+    // warp-per-game kernel but keeps the issue slots only 28 % busy (instruction-fetch stalls, 14 of 32 lanes active,
+    // 16 warps per SM), so it is the slower of the two (profiles/r2d_*).  ORX_KERNEL=lanes forces it;
+    // ORX_LANE_MIN_TOTAL=n uses it for batches of at least n playouts.
+    c->lane_min_total = ~0ull;
     if (const char *k = getenv("ORX_KERNEL")) c->kernel_choice = !strcmp(k, "warp") ? 1 : (!strcmp(k, "lanes") ? 2 : 0);
     if (const char *mt = getenv("ORX_LANE_MIN_TOTAL")) c->lane_min_total = strtoull(mt, nullptr, 10);
     return ORX_OK;
@@ -445,6 +448,21 @@ extern "C" int orx_set_sim_agents(OrxCtx *c, const int32_t *agent_ids, int model
 }
 
 extern "C" int orx_last_kernel_kind(const OrxCtx *c) { return c ? c->last_kernel : 0; }
+
+extern "C" int orx_kernel_info(const OrxCtx *c, uint64_t total_playouts, int32_t *kind, int32_t *blocks_per_sm,
+                               int32_t *threads_per_block, int32_t *smem_bytes_per_block)
+{
+    if (!c) return set_err(ORX_E_INVALID, "null context");
+    RolloutArgs ar;
+    memset(&ar, 0, sizeof ar);
+    ar.total = total_playouts;
+    const bool lanes = use_lane_kernel(c, false, ar);
+    if (kind) *kind = lanes ? 2 : 1;
+    if (blocks_per_sm) *blocks_per_sm = lanes ? c->lane_blocks_per_sm : c->blocks_per_sm[2 * (int)c->modelling];
+    if (threads_per_block) *threads_per_block = lanes ? ORX_LANE_THREADS : ORX_BLOCK_THREADS;
+    if (smem_bytes_per_block) *smem_bytes_per_block = (int32_t)(lanes ? c->lane_smem_bytes : c->smem_bytes);
+    return ORX_OK;
+}
 extern "C" int orx_leaf_stride(const OrxCtx *c) { return c ? c->dm.leaf_stride : ORX_E_INVALID; }
 extern "C" void *orx_stream(OrxCtx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t orx_kernel_launches(const OrxCtx *c) { return c ? c->launches : 0; }

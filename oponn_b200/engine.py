@@ -65,6 +65,7 @@ def load_library():
     L.orx_last_kernel_ms.argtypes = [vp]; L.orx_last_kernel_ms.restype = C.c_float
     L.orx_kernel_launches.argtypes = [vp]; L.orx_kernel_launches.restype = u64
     L.orx_last_kernel_kind.argtypes = [vp]; L.orx_last_kernel_kind.restype = C.c_int
+    L.orx_kernel_info.argtypes = [vp, u64, p(i32), p(i32), p(i32), p(i32)]; L.orx_kernel_info.restype = C.c_int
     L.orx_get_attack_outcomes.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]
     L.orx_get_attack_outcomes.restype = C.c_int
     L.orx_simulate_battles.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, u64, vp, vp]
@@ -82,7 +83,7 @@ def load_library():
 #: every symbol include/orx.h declares (checked by tests/test_abi.py)
 EXPORTS = ("orx_create", "orx_destroy", "orx_last_error", "orx_leaf_stride", "orx_rollout_batch",
            "orx_rollout_batch_device", "orx_rollout_begin", "orx_rollout_end", "orx_rollout_replay", "orx_sync", "orx_stream", "orx_last_kernel_ms",
-           "orx_kernel_launches", "orx_last_kernel_kind", "orx_get_attack_outcomes", "orx_simulate_battles", "orx_simulate_individual",
+           "orx_kernel_launches", "orx_last_kernel_kind", "orx_kernel_info", "orx_get_attack_outcomes", "orx_simulate_battles", "orx_simulate_individual",
            "orx_stream_draws", "orx_card_cash_value", "orx_set_sim_agents")
 
 
@@ -205,6 +206,13 @@ class RolloutEngine:
     def last_kernel_kind(self) -> str:
         """which rollout kernel the last launch used: "warp" (one warp per game) or "lanes" (one lane per game)"""
         return {1: "warp", 2: "lanes"}.get(int(self._L.orx_last_kernel_kind(self._h)), "none")
+
+    def kernel_info(self, total_playouts: int) -> dict:
+        """launch shape of the rollout kernel a batch of that many playouts would use (orx_kernel_info)"""
+        k, b, t, sm = (C.c_int32() for _ in range(4))
+        self._ck(self._L.orx_kernel_info(self._h, int(total_playouts), C.byref(k), C.byref(b), C.byref(t), C.byref(sm)))
+        return {"kernel": {1: "warp", 2: "lanes"}[k.value], "blocks_per_sm": b.value, "threads_per_block": t.value,
+                "smem_bytes_per_block": sm.value, "warps_per_sm": b.value * t.value // 32}
 
     @property
     def kernel_launches(self) -> int:

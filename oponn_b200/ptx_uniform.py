@@ -328,10 +328,16 @@ def analyse(lines: List[str], lo: int, hi: int) -> Tuple[List[int], int]:
         div_blocks |= new_div
 
 
-def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False, min_blocks: int = 0) -> str:
+#: the tuned all-SimRandom / counter-stream / <= 64-territory instantiation (gets ``min_blocks``; the others ``min_blocks_other``)
+MAIN_KERNEL = "rollout_kernelILi2ELb0ELb0E"
+
+
+def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False, min_blocks: int = 0, min_blocks_other: int = 0,
+              stats_out: list = None) -> str:
     """``min_blocks`` > 0 also rewrites ``.minnctapersm`` of the matching kernels: the front end is compiled with a
     loose ``__launch_bounds__`` (it produces markedly worse code under a tight register budget: 105k vs 158k
-    playouts/s measured) and only ptxas is given the tight one."""
+    playouts/s measured) and only ptxas is given the tight one.  ``min_blocks_other`` (default: the same) is the budget
+    of the instantiations other than MAIN_KERNEL (replay, modelled opponents, large maps: bigger code, fewer blocks fit)."""
     lines = ptx.split("\n")
     stats = []
     if min_blocks > 0:
@@ -341,7 +347,8 @@ def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False, min
             if m:
                 cur = m.group(2)
             if only in cur and ln.startswith(".minnctapersm"):
-                lines[n] = f".minnctapersm {min_blocks}"
+                mb = min_blocks if (MAIN_KERNEL in cur or not min_blocks_other) else min_blocks_other
+                lines[n] = f".minnctapersm {mb}"
     for lo, hi, name in split_functions(lines):
         if only not in name:
             continue
@@ -352,11 +359,20 @@ def transform(ptx: str, only: str = "rollout_kernel", verbose: bool = False, min
     if verbose:
         for name, u, t in stats:
             print(f"ptx_uniform: {name}: {u} of {t} conditional branches marked uniform", file=sys.stderr)
+    if stats_out is not None:
+        stats_out.extend(stats)
     return "\n".join(lines)
 
 
 if __name__ == "__main__":
+    # usage: ptx_uniform.py in.ptx out.ptx [min_blocks [min_blocks_other [stats.json]]]
     src, dst = sys.argv[1], sys.argv[2]
     mb = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    text = transform(open(src).read(), verbose=True, min_blocks=mb)   # read fully before (possibly) overwriting in place
+    mbo = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    st = []
+    text = transform(open(src).read(), verbose=True, min_blocks=mb, min_blocks_other=mbo, stats_out=st)   # read fully before (possibly) overwriting in place
     open(dst, "w").write(text)
+    if len(sys.argv) > 5:
+        import json
+        json.dump({"min_blocks": mb, "min_blocks_other": mbo, "bra_uni": text.count("bra.uni"),
+                   "kernels": {n: {"uniform": u, "conditional": t} for n, u, t in st}}, open(sys.argv[5], "w"), indent=1)

@@ -90,6 +90,23 @@ def main():
         print(k, v.shape, v.dtype.names if v.dtype.names else "")
 
 
+def workload_large(n: int = 2048):
+    """the same counters for the 200-territory map (BASELINE.json config 4) -> workload_synth200_mid_s1.json"""
+    import json
+    m, r = synth200(), Rules(max_player_turns=4096)
+    o = Oracle(m, r)
+    leaf = np.fromfile(os.path.join(HERE, "synth200_mid_s1.leaf"), dtype=np.uint8)
+    agg, games, ct = o.rollout_batch(leaf[None, :], n, RUN_SEED, per_game=True, threads=8, counters=True)
+    per = {k: v / n for k, v in ct.items()}
+    A = per["tv"] + per["ev"] + per["cdf_steps"] + per["writes"] + 16 * per["r_words"]
+    out = dict(leaf="synth200_mid_s1", run_seed=RUN_SEED, playouts=n, per_playout=per, algorithmic_int_ops_per_playout=A,
+               formula="A = TV + EV + L(cdf_steps) + W + 16*R(words)  (SURVEY.md 8d)", step_cap_player_turns=4096,
+               mean_sim_turn_count=float(games["sim_turn_count"].mean()), flagged=int(agg["flagged"][0]),
+               generated_by="python tests/golden/make_golden.py --workload-large  (oracle counters, 8 threads)")
+    json.dump(out, open(os.path.join(HERE, "workload_synth200_mid_s1.json"), "w"), indent=1)
+    print("A =", A, "flagged", int(agg["flagged"][0]))
+
+
 def workload(n: int = 16384):
     """Algorithmic work per playout of the bench leaf (A = TV + EV + L + W + 16 R), from the
     oracle's counters -> workload_classic42_mid_s1.json (read by bench.py for roofline.achieved)."""
@@ -157,7 +174,9 @@ def results_only():
 
 
 if __name__ == "__main__":
-    if "--results" in sys.argv:
+    if "--workload-large" in sys.argv:
+        workload_large()
+    elif "--results" in sys.argv:
         results_only()
     elif "--workload" in sys.argv:
         workload()

@@ -134,7 +134,8 @@ def test_all_playouts_of_a_leaf_get_the_same_hidden_hands():
 
 
 def test_auto_choice_and_agreement_of_the_two_kernels(monkeypatch):
-    """a large batch goes to the lane kernel on its own, and its aggregates equal the warp-per-game kernel's"""
+    """with ORX_LANE_MIN_TOTAL set, a large batch goes to the lane kernel and a small one does not; without it every
+    batch runs on the warp-per-game kernel; the two kernels' records are identical"""
     from oponn_b200.engine import RolloutEngine
     m = classic42(6)
     leaf = np.fromfile(os.path.join(GOLDEN, "classic42_mid_s1.leaf"), dtype=np.uint8)
@@ -146,7 +147,7 @@ def test_auto_choice_and_agreement_of_the_two_kernels(monkeypatch):
         assert e.last_kernel_kind == "lanes"
         small, _ = e.rollout_batch(leaf[None, :], 1024, 99, per_game=False)
         assert e.last_kernel_kind == "warp"
-    monkeypatch.setenv("ORX_KERNEL", "warp")
+    monkeypatch.delenv("ORX_LANE_MIN_TOTAL")
     with RolloutEngine(m, Rules(), 0) as e:
         agg2, games2 = e.rollout_batch(leaf[None, :], n, 99, per_game=True)
         assert e.last_kernel_kind == "warp"
