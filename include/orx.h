@@ -11,7 +11,8 @@
  * library owns its device scratch.  Every function returns 0 on success or a negative
  * ORX_E_* code (the reference throws unchecked exceptions instead -- SURVEY.md 8b).
  * A context is bound to one CUDA device and one stream; calls on one context must not
- * overlap, distinct contexts are independent.  There is no CPU fallback: without a usable
+ * overlap, distinct contexts are independent (launches of different contexts are serialised
+ * for the instant of the launch itself: the kernels' shared-memory size is set per launch).  There is no CPU fallback: without a usable
  * CUDA device orx_create fails with ORX_E_CUDA.
  */
 #ifndef ORX_H

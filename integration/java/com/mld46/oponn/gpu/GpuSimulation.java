@@ -43,6 +43,12 @@ public final class GpuSimulation implements AutoCloseable {
                         cardManager.getCardProgressionPos(), true);
         orx.rolloutGames(leaf, 1, cores, seed, gameCounter, games);   // orx_rollout_batch(..., agg = NULL, games)
         gameCounter += cores;
+        // the Java board throws on an illegal state (SimulationBoard.java:357,430,...); the engine flags the playout
+        // instead (ORX_FLAG_ERROR = 1) and zeroes its record: never back-propagate such a record
+        for (int j = 0; j < cores; j++) {
+            int flags = games.get(java.lang.foreign.ValueLayout.JAVA_INT, (long) GAME_RESULT_BYTES * j + 36);
+            if ((flags & 1) != 0) throw new IllegalStateException("rollout engine rejected the leaf record (ORX_FLAG_ERROR), playout " + j);
+        }
     }
 
     /** board.getPlayerOutOnTurn() of playout j (MCTSTree.java:409) */

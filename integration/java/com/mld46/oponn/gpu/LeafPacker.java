@@ -52,9 +52,16 @@ public final class LeafPacker {
         dst.set(JAVA_BYTE, 19, (byte) (attackUntilDead ? 1 : 0));
         dst.set(JAVA_BYTE, 20, (byte) hand.size());
         dst.set(JAVA_BYTE, 21, (byte) deck.size());
+        // CardManager.simReset re-creates its generator as `new Random(simDeck.hashCode())` on every setupState
+        // (CardManager.java:240-248): simDeck is a copy of notInHand, List.hashCode() depends only on the elements, so
+        // this IS the seed the reference would use; the engine deals from the same java.util.Random LCG (orx_state.h).
+        dst.set(JAVA_BYTE, 23, (byte) 0);                                   // ORX_DEAL_LEAF_LCG
+        dst.set(JAVA_INT_UNALIGNED, 24, new java.util.ArrayList<Card>(deck).hashCode());
         for (int cc = 0; cc < n; cc++) {
             Country c = bs.countries[cc];
             dst.set(JAVA_BYTE, offOwner + cc, c.getOwner() < 0 ? NONE : (byte) c.getOwner());
+            // an ATTACK / INVADE state carries the conquered country at 0 armies (ExplorationBoard after an invading
+            // AttackOutcome: finishAttack zeroed it, executeInvasion overwrites it): the record allows exactly that 0
             dst.set(JAVA_INT_UNALIGNED, offArmies + 4L * cc, c.getArmies());
         }
         for (int i = 0; i < p; i++) dst.set(JAVA_BYTE, offNcards + i, (byte) bs.playerNumberOfCards[i]);

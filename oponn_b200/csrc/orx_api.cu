@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,8 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
     } while (0)
 
 extern "C" const char *orx_last_error(void) { return g_err; }
+// for the other translation units of the library (orx_tree.cpp)
+__attribute__((visibility("hidden"))) void orx_internal_set_error(const char *text) { snprintf(g_err, sizeof g_err, "%s", text ? text : ""); }
 
 // ---------------------------------------------------------------------------------------------
 // BattleSim outcome tables (O/BattleSim.java:190-286), built on the device at context creation.
@@ -268,7 +271,7 @@ static cudaError_t configure_kernel(RolloutKernel k, size_t smem, int *blocks_pe
 static void layout_slice(OrxCtx *c, bool with_moveable)
 {
     DevMap &dm = c->dm;
-    int off = ORX_WARP_HDR_BYTES;
+    int off = ORX_WARP_HDR_BYTES + ORX_WARP_ACC_BYTES;   // header words, then the warp's running OrxLeafResult sums
     dm.w_rng = off;    off += 512;
     dm.w_armies = off; off += 4 * dm.NP;
     dm.w_owner = off;  off += dm.NP;
@@ -485,12 +488,17 @@ extern "C" float orx_last_kernel_ms(OrxCtx *c)
     return ms;
 }
 
+// The opt-in dynamic shared-memory size is an attribute of the kernel FUNCTION, not of a context: two contexts with
+// different maps (different sizes) driven from different host threads must not interleave "set attribute" and "launch".
+static std::mutex g_launch_mutex;
+
 // one launch of the rollout kernel on `stream` (default: the context's stream, bracketed by the timing events)
 static int launch_rollout(OrxCtx *c, bool replay, const RolloutArgs &ar, cudaStream_t stream = nullptr)
 {
     const bool timed = stream == nullptr;
     if (!stream) stream = c->stream;
     CK(cudaMemsetAsync(ar.ticket, 0, sizeof(unsigned long long), stream));
+    std::lock_guard<std::mutex> launch_lock(g_launch_mutex);
     if (use_lane_kernel(c, replay, ar)) {
         LaneArgs la;
         memset(&la, 0, sizeof la);

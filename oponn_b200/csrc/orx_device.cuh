@@ -26,8 +26,13 @@ __constant__ uint32_t c_magic[ORX_MAGIC_N];
 
 // per-warp header words (uint32 indices into the first 32 bytes of the slice)
 enum { WH_GAUSS_LO = 0, WH_GAUSS_HI = 1, WH_HAVE_GAUSS = 2, WH_G0 = 3, WH_G1 = 4, WH_SIM_START = 5, WH_REM_COUNTRIES = 6,
-       WH_DEAL_LO = 7, WH_DEAL_HI = 8, WH_DEAL_MODE = 9 };   // CardManager.random (48-bit java.util.Random state) + ORX_DEAL_*
+       WH_DEAL_LO = 7, WH_DEAL_HI = 8, WH_DEAL_MODE = 9, WH_CUR_LEAF = 10 };   // CardManager.random (48-bit java.util.Random state) + ORX_DEAL_*
 #define ORX_WARP_HDR_BYTES 48
+#ifdef ORX_ACC_PER_WARP
+#define ORX_WARP_ACC_BYTES 160   // 20 x u64: the image of one OrxLeafResult (rollout kernel: per-warp running sums)
+#else
+#define ORX_WARP_ACC_BYTES 0
+#endif
 
 __device__ __forceinline__ int lane_id() { int l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }

@@ -34,7 +34,7 @@ struct Game {
     const DevMap &dm;
     // 32-bit shared-window addresses: the static map image (per block) and this warp's slice
     saddr s_adj, s_deg, s_sym, s_nbr, s_cont, s_bonus;
-    saddr a_arm, a_own, a_alist, a_cards, a_hdr;
+    saddr a_arm, a_own, a_alist, a_cards, a_hdr;   // (the warp's running OrxLeafResult sums sit right behind the header)
     saddr a_move;             // MODEL: Country.moveableArmies, int32 per territory
     uint32_t agents;          // MODEL: ORX_AGENT_* of player p in bits 3p..3p+2 (simAgents[], ModellingBoard.java)
     Stream<REPLAY> s;
@@ -99,6 +99,21 @@ struct Game {
         int c = bytes_remove_at(list(li), n, i);
         if (lane == li) ncard--;
         return c;
+    }
+
+    // List.remove(Object): the first element equal to `card` (the caller knows it is there)
+    __device__ __forceinline__ void list_remove_value(int li, int card)
+    {
+        const int n = list_len(li);
+        const saddr p = list(li);
+        int at = -1;
+        for (int base = 0; base < n && at < 0; base += 32) {
+            const int i = base + lane;
+            const uint32_t m = __ballot_sync(ORX_FULL, i < n && (int)lds8(p + (uint32_t)(i < n ? i : 0)) == card);
+            if (m) at = base + __ffs(m) - 1;
+        }
+        if (at < 0) { fail(); return; }
+        list_remove_at(li, at);
     }
 
     // ---- board scans ------------------------------------------------------------------
@@ -206,7 +221,9 @@ struct Game {
     {
         saddr h = list(cp);
         int c0 = (int)lds8(h + (uint32_t)idx[0]), c1 = (int)lds8(h + (uint32_t)idx[1]), c2 = (int)lds8(h + (uint32_t)idx[2]);
-        list_remove_at(cp, idx[2]); list_remove_at(cp, idx[1]); list_remove_at(cp, idx[0]);
+        // currentCards.remove(card) x3 (:596-598): List.remove(Object) takes out the FIRST element equal to the card; the
+        // two wildcards are one object, so a triple holding the hand's second wildcard removes the first one
+        list_remove_value(cp, c0); list_remove_value(cp, c1); list_remove_value(cp, c2);
         list_add(dm.P, c0); list_add(dm.P, c1); list_add(dm.P, c2);  // CardManager.simCash :265-276
         placeable += card_cash_value(dm, cardpos, s.flags);
         cardpos++;
@@ -1140,14 +1157,39 @@ struct Game {
             if (lane < 12) ((uint32_t *)out)[lane] = v;
         }
         if (agg) {
-            unsigned long long *a = (unsigned long long *)agg;  // n, len_sum, wins[8], win_len_sum[8], flagged
-            if (lane < ORX_MAX_PLAYERS && my_pot == -1) {
-                atomicAdd(a + 2 + lane, 1ull);
-                atomicAdd(a + 10 + lane, (unsigned long long)(long long)turns);
-            }
+            // exact integer sums of this warp's playouts of the current leaf, kept in the warp's slice (lane l owns words
+            // 2l, 2l+1 of the OrxLeafResult image) and flushed with one atomic per non-zero field when the leaf changes
+            // or the warp retires (flush_leaf_sums): ~20 global atomics per warp instead of ~5 per playout
+#ifndef ORX_ACC_PER_WARP   // default: ~5 global atomics per playout on the leaf's record (the per-warp sums below cost 5 %: DESIGN.md 8)
+            unsigned long long *a = (unsigned long long *)agg;
+            if (lane < ORX_MAX_PLAYERS && my_pot == -1) { atomicAdd(a + 2 + lane, 1ull); atomicAdd(a + 10 + lane, (unsigned long long)(long long)turns); }
             if (lane == 8) { atomicAdd(a + 0, 1ull); atomicAdd(a + 1, (unsigned long long)(long long)turns); }
             if (lane == 9 && flags) atomicAdd(a + 18, 1ull);
+#else
+            if (lane < ORX_MAX_PLAYERS && my_pot == -1) { acc_add(2 + lane, 1u); acc_add(10 + lane, (uint32_t)turns); }
+            if (lane == 8) { acc_add(0, 1u); acc_add(1, (uint32_t)turns); }
+            if (lane == 9 && flags) acc_add(18, 1u);
+#endif
         }
+    }
+    // 64-bit add into field f of the warp's OrxLeafResult image (each field has exactly one writer lane)
+    __device__ __forceinline__ void acc_add(int f, uint32_t v)
+    {
+        const saddr p = a_hdr + (uint32_t)ORX_WARP_HDR_BYTES + 8u * (uint32_t)f;
+        uint32_t lo = lds32(p), hi = lds32(p + 4u);
+        const uint32_t nlo = lo + v;
+        hi += nlo < lo;
+        sts32(p, nlo); sts32(p + 4u, hi);
+    }
+    __device__ __forceinline__ void flush_leaf_sums(OrxLeafResult *agg)
+    {
+        __syncwarp();
+        if (lane < 20) {
+            const saddr p = a_hdr + (uint32_t)ORX_WARP_HDR_BYTES + 8u * (uint32_t)lane;
+            const unsigned long long v = ((unsigned long long)lds32(p + 4u) << 32) | (unsigned long long)lds32(p);
+            if (v) { atomicAdd((unsigned long long *)agg + lane, v); sts32(p, 0u); sts32(p + 4u, 0u); }
+        }
+        __syncwarp();
     }
 };
 
@@ -1183,6 +1225,11 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
     g.a_alist = wbase + (uint32_t)dm.w_alist; g.a_cards = wbase + (uint32_t)dm.w_cards;
     g.a_move = wbase + (uint32_t)dm.w_move; g.agents = 0u;
     const saddr rng = wbase + (uint32_t)dm.w_rng;
+#ifdef ORX_ACC_PER_WARP
+    if (g.lane < 20) { sts32(wbase + (uint32_t)ORX_WARP_HDR_BYTES + 8u * (uint32_t)g.lane, 0u); sts32(wbase + (uint32_t)ORX_WARP_HDR_BYTES + 8u * (uint32_t)g.lane + 4u, 0u); }
+    if (g.lane == 0) sts32(wbase + 4u * WH_CUR_LEAF, 0xFFFFFFFFu);   // the leaf the warp's running sums belong to: none yet
+    __syncwarp();
+#endif
 
     for (;;) {
         unsigned long long idx = 0;
@@ -1190,6 +1237,17 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
         idx = __shfl_sync(ORX_FULL, idx, 0);
         if (idx >= ar.total) break;
         unsigned long long leaf_i = REPLAY ? idx : idx / (unsigned long long)ar.playouts_per_leaf;
+#ifdef ORX_ACC_PER_WARP
+        if (ar.agg) {
+            const uint32_t cur = lds32(g.a_hdr + 4u * WH_CUR_LEAF);
+            if (cur != (uint32_t)leaf_i) {
+                if (cur != 0xFFFFFFFFu) g.flush_leaf_sums(ar.agg + cur);
+                __syncwarp();
+                if (g.lane == 0) sts32(g.a_hdr + 4u * WH_CUR_LEAF, (uint32_t)leaf_i);
+                __syncwarp();
+            }
+        }
+#endif
         const uint8_t *leaf = ar.leaves + leaf_i * (unsigned long long)dm.leaf_stride;
         g.s.init(rng, g.a_hdr, ar.seed, ar.first_game + idx,
                  REPLAY ? ar.words + idx * (unsigned long long)ar.words_per_game : nullptr, ar.words_per_game);
@@ -1199,6 +1257,12 @@ __global__ void __launch_bounds__(ORX_BLOCK_THREADS, ORX_MIN_BLOCKS) rollout_ker
         g.write_result(ar.games ? ar.games + idx : nullptr, ar.agg ? ar.agg + leaf_i : nullptr);
         __syncwarp();
     }
+#ifdef ORX_ACC_PER_WARP
+    if (ar.agg) {
+        const uint32_t cur = lds32(g.a_hdr + 4u * WH_CUR_LEAF);
+        if (cur != 0xFFFFFFFFu) g.flush_leaf_sums(ar.agg + cur);
+    }
+#endif
 }
 
 }  // namespace orx

@@ -503,7 +503,18 @@ struct Lane : LaneEnv, LaneState {
     {
         const uint8_t *h = list(cp);
         const int c0 = h[idx[0]], c1 = h[idx[1]], c2 = h[idx[2]];
-        list_remove_at(cp, idx[2]); list_remove_at(cp, idx[1]); list_remove_at(cp, idx[0]);
+        // currentCards.remove(card) x3 (:596-598): the FIRST element equal to the card (the two wildcards are one object)
+        const int cv[3] = { c0, c1, c2 };
+        LN_NOUNROLL
+        for (int q = 0; q < 3; q++) {
+            const uint8_t *hh = list(cp);
+            const int n = ncard(cp);
+            int at = -1;
+            LN_NOUNROLL
+            for (int i = 0; i < n; i++) if (hh[i] == cv[q]) { at = i; break; }
+            if (at < 0) { fail(); return; }
+            list_remove_at(cp, at);
+        }
         list_add(dm->P, c0); list_add(dm->P, c1); list_add(dm->P, c2);   // CardManager.simCash
         placeable += card_cash_value(cardpos);
         cardpos++;

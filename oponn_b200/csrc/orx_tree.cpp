@@ -27,6 +27,9 @@
 
 #include "../../include/orx_tree.h"
 
+// thread-local error text of liborx.so (orx_api.cu); not part of the C ABI
+__attribute__((visibility("hidden"))) void orx_internal_set_error(const char *text);
+
 namespace {
 
 enum { MAXP = ORX_MAX_PLAYERS, MAXC = ORX_MAX_CONTINENTS };
@@ -839,7 +842,7 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
     std::vector<Node> &nodes = t->nodes;
     nodes.clear();
     Board board(S, O);
-    if (!board.setup((const uint8_t *)root_leaf, (const uint8_t *)extra)) return ORX_E_INVALID;
+    if (!board.setup((const uint8_t *)root_leaf, (const uint8_t *)extra)) { orx_internal_set_error("orx_tree_search: the root leaf record is invalid"); return ORX_E_INVALID; }
     nodes.emplace_back();
     nodes[0].currentPlayer = O.agent_id;  // new SearchNode(agentID, numberOfPlayers) (:163)
     nodes[0].unvisited = board.possible_moves();
@@ -855,12 +858,20 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
     std::vector<OrxGameResult> games;
     const int slots = O.leaves_in_flight >= 2 ? 2 : 1;
     const int per_batch = std::max(1, O.leaves_in_flight / slots);
+    // Every early exit below (an illegal board, a failed launch, a failed copy) must leave the context usable: batches
+    // still in flight are ended (their results dropped) so that their slots are free for the next call.
+    struct Drain {
+        OrxCtx *ctx; Batch *b; bool armed = true;
+        ~Drain() { if (armed) for (int k = 0; k < 2; k++) if (b[k].outstanding && b[k].nleaf) { orx_rollout_end(ctx, k, nullptr, nullptr); b[k].outstanding = false; } }
+    } drain{ t->ctx, batch };
+    auto fail = [&](int code, const char *why) { orx_internal_set_error(why); return code; };
 
     auto finish = [&](int sl) -> int {
         Batch &B = batch[sl];
         auto t1 = clk::now();
         if (B.nleaf) {
             games.resize((size_t)B.nleaf * ppl);
+            B.outstanding = false;   // ended (successfully or not): nothing left to drain for this slot
             int rc = orx_rollout_end(t->ctx, sl, nullptr, games.data());
             if (rc != ORX_OK) return rc;
         }
@@ -953,7 +964,7 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
                 ongoing = board.update(nodes[pick].move);
                 cur = pick;
             }
-            if (board.error) return ORX_E_INVALID;
+            if (board.error) return fail(ORX_E_INVALID, "orx_tree_search: a move of the selection path is illegal on its board");
             if (ongoing && !nodes[cur].unvisited.empty()) {
                 // --- expansion (:335-355)
                 int k = rng.below((int)nodes[cur].unvisited.size());
@@ -964,8 +975,8 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
                 Node nn; nn.move = mv; nn.parent = cur; nn.depth = nodes[cur].depth + 1; nn.rootIndex = ri;
                 nn.currentPlayer = mv.type == ORX_MOVE_NEXT_PHASE ? mv.c : nodes[cur].currentPlayer;
                 ongoing = board.update(mv);
-                if (board.error) return ORX_E_INVALID;
-                if (ongoing) { nn.unvisited = board.possible_moves(); if (board.error || nn.unvisited.empty()) return ORX_E_INVALID; }
+                if (board.error) return fail(ORX_E_INVALID, "orx_tree_search: the expanded move is illegal on its board");
+                if (ongoing) { nn.unvisited = board.possible_moves(); if (board.error || nn.unvisited.empty()) return fail(ORX_E_INVALID, "orx_tree_search: an ongoing position has no legal move"); }
                 int id = (int)nodes.size();
                 nodes.push_back(nn);
                 nodes[cur].children.push_back(id);
@@ -1003,6 +1014,7 @@ extern "C" int orx_tree_search(OrxTree *t, const void *root_leaf, const void *ex
         }
         if (slots == 2) sl ^= 1;
     }
+    drain.armed = false;
     st.iterations = done; st.playouts = (int64_t)done * ppl; st.nodes = (int64_t)nodes.size();
     if (stats) *stats = st;
     // root children in getPossibleMoves() order

@@ -798,9 +798,15 @@ static int cashCards(Board *b, const int idx[3])
     CardList *hand = &b->playerCards[b->currentPlayer];
     uint8_t c[3] = { hand->v[idx[0]], hand->v[idx[1]], hand->v[idx[2]] };
     if (!isASet(b, c[0], c[1], c[2])) return 0;
-    /* currentCards.remove(card) x3: the triple names distinct positions, and the two
-     * wildcards are one object, so removing by position (high to low) is the same list */
-    list_remove_at(hand, idx[2]); list_remove_at(hand, idx[1]); list_remove_at(hand, idx[0]);
+    /* currentCards.remove(card1); remove(card2); remove(card3) (:596-598): List.remove(Object) takes out the FIRST
+     * element equal to the card.  Territory cards are unique, but the two wildcards are one static object
+     * (CardManager.java:14,62-63): a triple that holds the hand's second wildcard removes the first one. */
+    for (int q = 0; q < 3; q++) {
+        int at = -1;
+        for (int i = 0; i < hand->n && at < 0; i++) if (hand->v[i] == c[q]) at = i;
+        if (at < 0) { FAIL(b); return 0; }
+        list_remove_at(hand, at);
+    }
     /* CardManager.simCash (O/CardManager.java:265-276) */
     list_add(&b->simDeck, c[0]); list_add(&b->simDeck, c[1]); list_add(&b->simDeck, c[2]);
     /* engine limit: only the exponential ("%") progressions are table driven on the device */

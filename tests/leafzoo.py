@@ -70,7 +70,13 @@ def phase_zoo(m, base: np.ndarray = None, seed: int = 3):
     a, d = _enemy_pair(m, b, cp)
     b.armies[a] = max(b.armies[a], 6)
     b.attackingCC, b.defendingCC, b.defendingPlayer = a, d, b.owner[d]
-    b.owner[d] = cp; b.armies[d] = 1   # armies are overwritten by executeInvasion; the record needs armies >= 1
+    b.owner[d] = cp; b.armies[d] = 1   # armies are overwritten by executeInvasion
+    # the same as ExplorationBoard.getBoardState() really leaves it: the conquered country at 0 armies
+    b = add("attack_invade_zero_armies", currentPhase=PHASE_ATTACK, attackState=ATTACK_INVADE, hasInvadedACountry=False)
+    a, d = _enemy_pair(m, b, cp)
+    b.armies[a] = max(b.armies[a], 9)
+    b.attackingCC, b.defendingCC, b.defendingPlayer = a, d, b.owner[d]
+    b.owner[d] = cp; b.armies[d] = 0
     add("attack_cash", currentPhase=PHASE_ATTACK, attackState=ATTACK_CASH, numberOfPlaceableArmies=0,
         hand=[0, 1, 2, 3, 4, 5])
     add("attack_place", currentPhase=PHASE_ATTACK, attackState=ATTACK_PLACE, numberOfPlaceableArmies=11)

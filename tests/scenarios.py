@@ -90,7 +90,129 @@ def scenario_cards_and_income():
     return m, r, leaf, s.array(pad=4), exp
 
 
-ALL = [scenario_sweep, scenario_catchup_execute_keeps_owner, scenario_cards_and_income]
+def scenario_overflow_crowns_the_new_current_player():
+    """SURVEY 8.1 quirks 5 and 6.  A FORTIFICATION leaf above 100 000 armies: tearDownFortificationPhase advances
+    currentPlayer FIRST (SimulationBoard.java:972-978), then checkForOverflow (:984-1015) defeats everybody but the
+    largest holder "by" that holder, and playerDefeated writes the winner flag to currentPlayer (:862-866) -- the player
+    who has just been defeated.  Player 2 owns nothing at the leaf: never alive in the playout, its entry stays 0.
+    No random draw at all."""
+    m, r = line4(3), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[60000, 1, 50000, 1], currentPlayer=0, currentPhase=PHASE_FORTIFICATION,
+                      playerNumberOfCards=[0, 0, 0])
+    s = Script()
+    # getNextPlayer: 1 (not a wrap: simTurnCount stays 0); totals 60001 / 50001 / 0 -> 110002 > 100000, maxPlayer = 0;
+    # playerDefeated(1, 0): remainingPlayers 2 -> 1, playerOutOnTurn[1] = 0, then playerOutOnTurn[currentPlayer = 1] = -1
+    exp = dict(pot=[0, -1, 0], turns=0, flags=0, stream_pos=0, hash=board_hash([0, 0, 1, 1], [60000, 1, 50000, 1]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_invade_leaf_counts_the_vanquished_player():
+    """An ATTACK / INVADE leaf whose conquered country was the defender's last: the tree has already moved ownership
+    (ExplorationBoard.java:174-177), the record carries the country at 0 armies, and setupPhaseGameState bumps
+    remainingPlayers (SimulationBoard.java:339-342) so that finishInvasion can defeat the player and crown the attacker."""
+    from oponn_b200.state import ATTACK_INVADE
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 0, 0], armies=[1, 5, 0, 1], currentPlayer=0, currentPhase=PHASE_ATTACK, attackState=ATTACK_INVADE,
+                      attackingCC=1, defendingCC=2, defendingPlayer=1, playerNumberOfCards=[0, 0])
+    s = Script()
+    s.int(1, 0)                    # moveArmiesIn: avail 4, min 3, 3 + nextInt(1) = 3 -> armies [1, 2, 3, 1]
+    term = len(s.words)            # finishInvasion: playerCountries[1] == 0 -> defeated, playerOutOnTurn[0] = -1
+    # attackPhase: nobody has an enemy neighbour -> empty list; no cards; FORTIFICATION is never played
+    exp = dict(pot=[-1, 0], turns=0, flags=0, stream_pos=term, hash=board_hash([0, 0, 0, 0], [1, 2, 3, 1]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_single_roll_catchup():
+    """a board whose attackUntilDead bit is still false resolves the pending EXECUTE attack with ONE
+    roll of min(a, 3) v min(d, 2) dice (SimulationBoard.java:758-780, BattleSim.java:152-162), not with a battle."""
+    m, r = line4(), Rules(use_cards=False, max_player_turns=1)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 2, 2, 3], currentPlayer=0, currentPhase=PHASE_ATTACK, attackState=ATTACK_EXECUTE,
+                      attackingCC=1, defendingCC=2, defendingPlayer=1, attackUntilDead=False, playerNumberOfCards=[0, 0])
+    assert first_row(1, 1) == (1, 0, False)
+    s = Script()
+    s.double_k(0)                  # 1 v 2 dice, r = 0 <= 0.2546: the attacker loses 0, the defender min(1, 2) - 0 = 1 -> armies[2] = 1
+    s.int(1, 0).int(1, 0)          # attackPhase: attackers [1] (2 armies); defenders [2]
+    s.double_k(0)                  # battle 1 v 1 till dead: first row = the attacker dies -> armies[1] = 1, list empty
+    # no conquest; FORTIFICATION -> player 1; one player-turn played: step limit
+    exp = dict(pot=[0, 0], turns=0, flags=2, stream_pos=len(s.words), hash=board_hash([0, 0, 1, 1], [1, 1, 1, 3]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_gaussian_battle_in_a_game():
+    """Both sides above 500: the closed form with one nextGaussian() (BattleSim.java:71-93).  The polar method is fed
+    nextDouble() = 0.5 and 0.75: v1 = 0, v2 = 0.5, s = 0.25 -> the first gaussian is exactly 0, variance = (int)(0 * sqrt) = 0.
+    600 v 600: matched = (int)(0.922 * 600) = 553 <= 600 -> all 600 defenders die, the attacker loses min(0 + 553, 599)."""
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 601, 600, 1], currentPlayer=0, currentPhase=PHASE_ATTACK, playerNumberOfCards=[0, 0])
+    assert first_row(2, 1) == (0, 1, True)
+    s = Script()
+    s.int(1, 0).int(1, 0)          # attackers [1]; defenders [2]
+    s.double(0.5).double(0.75)     # nextGaussian: one accepted pair, value 0
+    s.int(44, 0)                   # conquered: armies[1] = 601 - 553 = 48, avail 47, 3 + nextInt(44) = 3 -> armies [1, 45, 3, 1]
+    s.int(2, 1).int(1, 0)          # attackers [1, 2] -> A = 2; defenders [3]
+    s.double_k(0)                  # 2 v 1 -> (0, 1): conquered; avail 2 = min -> both move: armies [1, 45, 1, 2]; player 1 is out
+    term = len(s.words)
+    s.int(2, 0).int(1, 0)          # list [1, 3] (2 left with one army, 3 appended): both have no defender -> removed
+    exp = dict(pot=[-1, 0], turns=0, flags=0, stream_pos=term, hash=board_hash([0, 0, 0, 0], [1, 45, 1, 2]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def scenario_single_rolls_above_100_in_a_game():
+    """One side above 100: single rolls until a side is out or both fit the tables (BattleSim.java:99-116).  101 v 1 is
+    one roll of 3 v 1 dice; r = 0 <= 0.6597: the defender loses its army, no table draw follows."""
+    m, r = line4(), Rules(use_cards=False)
+    leaf = BoardState(owner=[0, 0, 1, 1], armies=[1, 102, 1, 1], currentPlayer=0, currentPhase=PHASE_ATTACK, playerNumberOfCards=[0, 0])
+    s = Script()
+    s.int(1, 0).int(1, 0)          # attackers [1]; defenders [2]
+    s.double_k(0)                  # the single roll
+    s.int(98, 0)                   # conquered: avail 101, 3 + nextInt(98) = 3 -> armies [1, 99, 3, 1]
+    s.int(2, 1).int(1, 0)          # A = 2; defenders [3]
+    s.double_k(0)                  # 2 v 1 -> conquered, both armies move: [1, 99, 1, 2]; player 1 is out
+    term = len(s.words)
+    s.int(2, 0).int(1, 0)
+    exp = dict(pot=[-1, 0], turns=0, flags=0, stream_pos=term, hash=board_hash([0, 0, 0, 0], [1, 99, 1, 2]))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+def line24():
+    n = 24
+    return RiskMap(name="line24", n_players=2, adjacency=[[x for x in (t - 1, t + 1) if 0 <= x < n] for t in range(n)],
+                   continent=[0] * n, continent_bonus=[7])
+
+
+def scenario_big_hand_forced_cashing_and_the_deal():
+    """SURVEY 8.1 quirks 8, 13, 15 on a 24-territory line, deals scripted through the game stream (ORX_DEAL_GAME_STREAM).
+    An 8-card hand of one symbol (codes 0, 3, ... 21: code % 3 == 0, every triple is a set): SimRandom.cardsPhase always
+    cashes with 5 or more cards, tearDownCardsPhase keeps cashing until 4 or fewer are left (SimulationBoard.java:620-638);
+    each cashed card whose country the player owns is worth +2 armies there (:605-616); a conquest earns one card at the
+    end of the attack phase, drawn from the sim deck the cashed cards went back to (:884-896, CardManager.java:250-276)."""
+    m, r = line24(), Rules(use_cards=True, transfer_cards=True, card_progression="0", max_player_turns=1)
+    hand = [0, 3, 6, 9, 12, 15, 18, 21]
+    deck = [c for c in range(24) if c not in hand] + [CARD_WILD, CARD_WILD]
+    leaf = BoardState(owner=[0] * 9 + [1] * 15, armies=[1] * 24, currentPlayer=0, currentPhase=PHASE_CARDS, playerNumberOfCards=[8, 0],
+                      cardProgressionPos=1, hand=hand, deck=deck, dealFromStream=True)
+    assert first_row(3, 1) == (0, 1, True) and first_row(2, 1) == (0, 1, True) and first_row(1, 1) == (1, 0, False)
+    s = Script()
+    s.double(0.9)                  # cardsPhase draws r even though 8 cards always cash (SimRandom.java:43-44)
+    s.int(56, 0)                   # getRandomSet: C(8,3) = 56 valid triples, the first is cards 0, 3, 6 -> +2 on countries 0, 3, 6 (owned)
+    s.int(10, 9)                   # forced: 5 cards left, C(5,3) = 10 triples, the last is cards 15, 18, 21 (not owned: no bonus)
+    # hand [9, 12]; progression "0": both sets are worth 0; income = max(9 / 3, 3) = 3, the continent is not owned
+    s.int(3, 2).int(1, 0)          # place 1 + 2 = 3 on the only border country, 8: armies[8] = 4
+    s.int(1, 0).int(1, 0)          # attackers [8] (0, 3 and 6 hold 3 armies but touch no enemy); defenders of 8: [9]
+    s.double_k(0)                  # 3 v 1 -> conquered; avail 3 = min: all three move, armies[8] = 1, armies[9] = 3
+    s.int(1, 0).int(1, 0)          # list [9]; defenders [10]
+    s.double_k(0)                  # 2 v 1 -> conquered; both move: armies[9] = 1, armies[10] = 2
+    s.int(1, 0).int(1, 0)          # list [10]; defenders [11]
+    s.double_k(0)                  # 1 v 1: the likelier row is the attacker's loss: armies[10] = 1, list empty
+    s.int(24, 23)                  # tearDownAttackPhase: one card from the 18 + 3 + 3 = 24 of the deck: the last one, card 21
+    armies = [3, 1, 1, 3, 1, 1, 3] + [1] * 17
+    exp = dict(pot=[0, 0], turns=0, flags=2, stream_pos=len(s.words), hash=board_hash([0] * 11 + [1] * 13, armies))
+    return m, r, leaf, s.array(pad=4), exp
+
+
+ALL = [scenario_sweep, scenario_catchup_execute_keeps_owner, scenario_cards_and_income, scenario_overflow_crowns_the_new_current_player,
+       scenario_invade_leaf_counts_the_vanquished_player, scenario_single_roll_catchup, scenario_gaussian_battle_in_a_game,
+       scenario_single_rolls_above_100_in_a_game, scenario_big_hand_forced_cashing_and_the_deal]
 
 
 # ---- modelled opponents (SURVEY 8(f) f4): (map, rules, leaf, words, expected, agent ids, modelling turn limit) --------
