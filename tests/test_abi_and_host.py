@@ -160,3 +160,20 @@ def test_maps_are_well_formed():
     assert sum(len(a) for a in c.adjacency) // 2 == 83
     s = synth200()
     assert (s.n_territories, s.n_continents, s.n_players) == (200, 10, 8)
+
+
+def test_oponn_txt_settings(tmp_path):
+    """Oponn.readSettings (Oponn.java:464-533): same keys, same parsing quirks"""
+    from oponn_b200.settings import read_settings, search_options
+    p = tmp_path / "Oponn.txt"
+    p.write_text("# comment\nlux_agent_modelling=false\niterations = 5 000\ncores=n\ndebug=true\nnonsense\n")
+    s = read_settings(str(p), available_cores=16)
+    assert (s.opponent_modelling, s.iterations, s.cores, s.debugging) == (False, 5000, 16, True)
+    p.write_text("lux_agent_modelling=no\niterations=many\ncores=4\n")
+    s = read_settings(str(p), available_cores=16)
+    assert (s.opponent_modelling, s.iterations, s.cores, s.debugging) == (True, 1000, 4, False)
+    assert search_options(s) == {"iterations": 250, "playouts_per_leaf": 4, "modelling_turn_limit": 2}
+    assert read_settings(str(tmp_path / "missing.txt"), available_cores=8).iterations == 1000
+    if os.path.exists("/root/reference/Oponn.txt"):           # the reference's own example file (not present on the GPU box)
+        s = read_settings("/root/reference/Oponn.txt", available_cores=8)
+        assert (s.opponent_modelling, s.iterations, s.cores, s.debugging) == (True, 1000, 8, False)
