@@ -146,12 +146,12 @@ static const int kTableRows = 2 * ORX_TABLE_LIMIT * (ORX_TABLE_LIMIT * (ORX_TABL
 __global__ void battles_kernel(const __grid_constant__ DevMap dm, int a, int d, int n, unsigned long long seed,
                                unsigned long long first_game, int individual, int32_t *al_out, int32_t *dl_out)
 {
-    __shared__ __align__(16) uint32_t sm[4][128 + 8];
+    __shared__ __align__(16) uint32_t sm[4][128 + 16];   // 16 header words, then the 128-word block
     int wid = threadIdx.x >> 5;
     long long i = (long long)blockIdx.x * 4 + wid;
     if (i >= n) return;
     Stream<false> s;
-    s.init(to_saddr(sm[wid] + 8), to_saddr(sm[wid]), seed, first_game + (unsigned long long)i, nullptr, 0);
+    s.init(to_saddr(sm[wid] + 16), to_saddr(sm[wid]), seed, first_game + (unsigned long long)i, nullptr, 0);
     int al = 0, dl = 0;
     uint32_t rk[20];
 #pragma unroll
@@ -169,9 +169,9 @@ template <bool REPLAY>
 __global__ void draws_kernel(unsigned long long seed, unsigned long long game, const uint32_t *words, uint32_t n_words,
                              const int32_t *ops, int n_ops, double *out, uint32_t *pos_flags)
 {
-    __shared__ __align__(16) uint32_t sm[128 + 8];
+    __shared__ __align__(16) uint32_t sm[128 + 16];
     Stream<REPLAY> s;
-    s.init(to_saddr(sm + 8), to_saddr(sm), seed, game, words, n_words);
+    s.init(to_saddr(sm + 16), to_saddr(sm), seed, game, words, n_words);
     for (int i = 0; i < n_ops; i++) {
         int op = ops[i];
         double v;

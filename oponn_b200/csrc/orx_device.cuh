@@ -71,6 +71,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 // all 32 lanes evaluate one Philox counter each: 128 consecutive words, lane l owning words 4l .. 4l+3 (orx_state.h)
+#ifndef ORX_V_REFILL_OLD   // the refill reads the game id from the warp header itself: two arguments fewer at every word() site (+4 %)
+__device__ __noinline__ void philox_refill_h(saddr buf, saddr hdr, uint32_t blk, uint32_t k0, uint32_t k1)
+{
+    uint32_t o[4];
+    int l = lane_id();
+    philox4x32_10(blk * 32u + (uint32_t)l, 0u, lds32(hdr + 12u), lds32(hdr + 16u), k0, k1, o);
+    __syncwarp();
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(buf + 16u * (uint32_t)l), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    __syncwarp();
+}
+#define ORX_REFILL(buf, hdr, blk, k0, k1) philox_refill_h(buf, hdr, blk, k0, k1)
+#else
+#define ORX_REFILL(buf, hdr, blk, k0, k1) philox_refill(buf, blk, lds32(hdr + 4 * WH_G0), lds32(hdr + 4 * WH_G1), k0, k1)
+#endif
 __device__ __noinline__ void philox_refill(saddr buf, uint32_t blk, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1)
 {
     uint32_t o[4];
@@ -100,7 +114,9 @@ struct Stream {
         buf = b; hdr = h; wi = 128u; base = REPLAY ? 0u : (uint32_t)-128; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         words = w; n_words = nw; flags = 0;
         __syncwarp();
-        if (lane_id() == 0) { sts32(h + 4 * WH_G0, (uint32_t)game); sts32(h + 4 * WH_G1, (uint32_t)(game >> 32)); sts32(h + 4 * WH_HAVE_GAUSS, 0u); }
+        if (lane_id() == 0) {
+            sts32(h + 4 * WH_G0, (uint32_t)game); sts32(h + 4 * WH_G1, (uint32_t)(game >> 32)); sts32(h + 4 * WH_HAVE_GAUSS, 0u);
+        }
         __syncwarp();
     }
 
@@ -109,7 +125,7 @@ struct Stream {
     __device__ __forceinline__ void refill()
     {
         base += 128u;
-        philox_refill(buf, base >> 7, lds32(hdr + 4 * WH_G0), lds32(hdr + 4 * WH_G1), k0, k1);
+        ORX_REFILL(buf, hdr, base >> 7, k0, k1);
         wi = 0u;
     }
 
@@ -118,7 +134,7 @@ struct Stream {
     {
         if (p - base < 128u) { wi = p - base; return; }
         base = p & ~127u;
-        philox_refill(buf, base >> 7, lds32(hdr + 4 * WH_G0), lds32(hdr + 4 * WH_G1), k0, k1);
+        ORX_REFILL(buf, hdr, base >> 7, k0, k1);
         wi = p & 127u;
     }
 
@@ -135,7 +151,8 @@ struct Stream {
         return v;
     }
 
-    // java.util.Random.nextInt(int bound)
+    // java.util.Random.nextInt(int bound).  SMALL: the caller knows bound < ORX_MAGIC_N (list lengths, neighbour counts)
+    template <bool SMALL = false>
     __device__ __forceinline__ int next_int(int bound)
     {
         if (bound <= 0) { flags |= ORX_FLAG_ERROR; return 0; }
@@ -144,7 +161,7 @@ struct Stream {
         if ((b & m) == 0u) return (int)(((unsigned long long)b * u) >> 31);
         for (;;) {
             uint32_t r;
-            if (b < (uint32_t)ORX_MAGIC_N) {  // u % b by multiplication: the estimate is q or q + 1
+            if (SMALL || b < (uint32_t)ORX_MAGIC_N) {  // u % b by multiplication: the estimate is q or q + 1
                 uint32_t q = __umulhi(u, c_magic[b]);
                 r = u - q * b;
                 if ((int)r < 0) r += b;

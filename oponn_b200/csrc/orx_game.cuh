@@ -29,6 +29,38 @@ struct RolloutArgs {
     uint32_t rk[20];              // Philox round keys of `seed`: rk[2r] = seed_lo + r * 0x9E3779B9, rk[2r+1] = seed_hi + r * 0xBB67AE85
 };
 
+// The hand positions cashCards really removes for the triple i0 < i1 < i2 (packed i0 | i1 << 8 | i2 << 16) of the n-card hand
+// at h: List.remove(Object) takes the first element EQUAL to the card, and the two wildcards are one object
+// (CardManager.java:14,62-63) -- a triple with exactly one wildcard that is not the hand's first wildcard removes the first
+// one instead.  Out of line on purpose: a once-per-cash fix whose registers must not weigh on the kernel's hot loops
+// (inlined it cost 7 % of the whole kernel).
+static __device__ __noinline__ uint32_t cash_indices(saddr h, int n, uint32_t pk)
+{
+    const int lane = lane_id();
+    int i0 = (int)(pk & 0xFFu), i1 = (int)((pk >> 8) & 0xFFu), i2 = (int)(pk >> 16);
+    int fw = -1;   // position of the hand's first wildcard
+    for (int base = 0; base < n && fw < 0; base += 32) {
+        const int i = base + lane;
+        const uint32_t m = __ballot_sync(ORX_FULL, i < n && lds8(h + (uint32_t)(i < n ? i : 0)) == ORX_CARD_WILD);
+        if (m) fw = base + __ffs(m) - 1;
+    }
+    if (fw < 0 || fw == i0 || fw == i1 || fw == i2) return pk;
+    // exactly one wildcard in the triple and it is the later one: fw replaces it (fw is smaller than the index it replaces)
+    if (lds8(h + (uint32_t)i0) == ORX_CARD_WILD) i0 = fw; else if (lds8(h + (uint32_t)i1) == ORX_CARD_WILD) i1 = fw; else i2 = fw;
+    int t;
+    if (i1 < i0) { t = i0; i0 = i1; i1 = t; }
+    if (i2 < i1) { t = i1; i1 = i2; i2 = t; }
+    if (i1 < i0) { t = i0; i0 = i1; i1 = t; }
+    return (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)i2 << 16);
+}
+
+// nextInt sites whose bound is a list length or a neighbour count (< ORX_MAGIC_N): the general division is compiled out there
+#ifdef ORX_V_SMALLINT_OFF
+#define ORX_NI_SMALL false
+#else
+#define ORX_NI_SMALL true
+#endif
+
 template <int NWT, bool REPLAY, bool MODEL = false>
 struct Game {
     const DevMap &dm;
@@ -99,21 +131,6 @@ struct Game {
         int c = bytes_remove_at(list(li), n, i);
         if (lane == li) ncard--;
         return c;
-    }
-
-    // List.remove(Object): the first element equal to `card` (the caller knows it is there)
-    __device__ __forceinline__ void list_remove_value(int li, int card)
-    {
-        const int n = list_len(li);
-        const saddr p = list(li);
-        int at = -1;
-        for (int base = 0; base < n && at < 0; base += 32) {
-            const int i = base + lane;
-            const uint32_t m = __ballot_sync(ORX_FULL, i < n && (int)lds8(p + (uint32_t)(i < n ? i : 0)) == card);
-            if (m) at = base + __ffs(m) - 1;
-        }
-        if (at < 0) { fail(); return; }
-        list_remove_at(li, at);
     }
 
     // ---- board scans ------------------------------------------------------------------
@@ -221,9 +238,13 @@ struct Game {
     {
         saddr h = list(cp);
         int c0 = (int)lds8(h + (uint32_t)idx[0]), c1 = (int)lds8(h + (uint32_t)idx[1]), c2 = (int)lds8(h + (uint32_t)idx[2]);
-        // currentCards.remove(card) x3 (:596-598): List.remove(Object) takes out the FIRST element equal to the card; the
-        // two wildcards are one object, so a triple holding the hand's second wildcard removes the first one
-        list_remove_value(cp, c0); list_remove_value(cp, c1); list_remove_value(cp, c2);
+        // currentCards.remove(card) x3 (:596-598): List.remove(Object) takes out the FIRST element equal to the card.
+        // Territory cards are unique; the two wildcards are one object, so a triple that holds the hand's SECOND wildcard
+        // but not the first removes the first one (cash_indices, out of line); then remove by position from the back.
+        uint32_t pk = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16);
+        if (c0 == (int)ORX_CARD_WILD || c1 == (int)ORX_CARD_WILD || c2 == (int)ORX_CARD_WILD)
+            pk = __shfl_sync(ORX_FULL, cash_indices(h, list_len(cp), pk), 0);   // (the shuffle tells the PTX pass the value is warp-uniform)
+        list_remove_at(cp, (int)(pk >> 16)); list_remove_at(cp, (int)((pk >> 8) & 0xFFu)); list_remove_at(cp, (int)(pk & 0xFFu));
         list_add(dm.P, c0); list_add(dm.P, c1); list_add(dm.P, c2);  // CardManager.simCash :265-276
         placeable += card_cash_value(dm, cardpos, s.flags);
         cardpos++;
@@ -275,7 +296,7 @@ struct Game {
         int n = count_bits(cand);
         while (n_armies > 0 && !s.flags) {
             int k = 1 + s.next_int(n_armies);
-            int i = s.next_int(n);
+            int i = s.template next_int<ORX_NI_SMALL>(n);
             if (s.flags) return;
             int t = nth_territory(cand, i);
             set_armies(t, armies(t) + k);
@@ -467,7 +488,7 @@ struct Game {
         attackUntilDead = 1;
         const int me = cp;
         while (L.n > 0 && !s.flags) {
-            int ai = s.next_int(L.n);
+            int ai = s.template next_int<ORX_NI_SMALL>(L.n);
             int A = alist_get(L, ai);
             // possibleDefenders: non-owned out-neighbours in getAdjoiningList() order
             int dg = deg(A);
@@ -476,7 +497,7 @@ struct Game {
             if (lane < dg) { nb = adj(A, lane); enemy = owner(nb) != me; }
             uint32_t dmask = __ballot_sync(ORX_FULL, enemy);
             if (dmask == 0u) { alist_remove(L, ai); continue; }
-            int D = from_lane(nb, nth_bit(dmask, s.next_int(__popc(dmask))));
+            int D = from_lane(nb, nth_bit(dmask, s.template next_int<ORX_NI_SMALL>(__popc(dmask))));
             // SimulationBoard.attack: setupAttack, executeAttack, finishAttack
             saddr pA = a_arm + 4u * (uint32_t)A, pD = a_arm + 4u * (uint32_t)D;
             int aArm = (int)lds32(pA), dArm = (int)lds32(pD);

@@ -65,7 +65,8 @@ def load_library():
     L.orx_last_kernel_ms.argtypes = [vp]; L.orx_last_kernel_ms.restype = C.c_float
     L.orx_kernel_launches.argtypes = [vp]; L.orx_kernel_launches.restype = u64
     L.orx_last_kernel_kind.argtypes = [vp]; L.orx_last_kernel_kind.restype = C.c_int
-    L.orx_kernel_info.argtypes = [vp, u64, p(i32), p(i32), p(i32), p(i32)]; L.orx_kernel_info.restype = C.c_int
+    if hasattr(L, "orx_kernel_info"):   # (absent from libraries built before round 2: variant timing only)
+        L.orx_kernel_info.argtypes = [vp, u64, p(i32), p(i32), p(i32), p(i32)]; L.orx_kernel_info.restype = C.c_int
     L.orx_get_attack_outcomes.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]
     L.orx_get_attack_outcomes.restype = C.c_int
     L.orx_simulate_battles.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, u64, vp, vp]
