@@ -443,6 +443,30 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
                     const int l = lane_id();
                     const saddr p0 = s.buf + 4u * s.wi + 8u * (uint32_t)l;
                     const int hi = ra < rd ? rd : ra;
+#ifdef ORX_V_SPEC
+                    // Speculative block: play ALL the doubles left in the block at once and look at the state after the last
+                    // of them.  Armies only fall, so if that state still has 3 v 2 dice and a side above 100, every state before
+                    // it had too: the rolls were exactly the reference's.  Otherwise nothing is committed and the scan below
+                    // finds the stopping roll.  Tried when the expected losses (about one army per side per roll) leave room.
+                    if (ra - avail >= 3 && rd - avail >= 2 && (hi - avail > 100 || ra + rd - 2 * avail > 200)) {
+                        int x = 0;
+                        if (l < avail) {
+                            uint64_t k = ((uint64_t)(lds32(p0) >> 6) << 27) + (uint64_t)(lds32(p0 + 4u) >> 5);
+                            x = (k > t0) + (k > t1);
+                        }
+                        if (l + 32 < avail) {
+                            uint64_t k = ((uint64_t)(lds32(p0 + 256u) >> 6) << 27) + (uint64_t)(lds32(p0 + 260u) >> 5);
+                            x += (k > t0) + (k > t1);
+                        }
+                        const int la = (int)__reduce_add_sync(ORX_FULL, (unsigned)x), ld = 2 * avail - la;
+                        const int ra2 = ra - la, rd2 = rd - ld;
+                        if ((ra2 > 100 || rd2 > 100) && ra2 >= 3 && rd2 >= 2) {
+                            ra = ra2; rd = rd2;
+                            s.wi += 2u * (uint32_t)avail;
+                            continue;
+                        }
+                    }
+#else
                     const int slack = 2 * (avail - 1);  // armies lost before the last roll of the step, at most
                     if (avail >= 32 && ra - slack >= 3 && rd - slack >= 2 && hi - slack > 100) {
                         int x = 0;
@@ -459,6 +483,7 @@ __device__ __forceinline__ void simulate_battle(const DevMap &dm, Stream<REPLAY>
                         s.wi += 2u * (uint32_t)avail;
                         continue;
                     }
+#endif
                     const int np = avail > 32 ? 32 : avail;
                     int x = 0;
                     if (l < np) {

@@ -37,7 +37,7 @@ def main():
             wins = [int(x) for x in agg["wins"][0][:6]]
             if ref is None:
                 ref = wins
-            print(f"{t:40s} kernel={e.last_kernel_kind:5s} {ms:10.1f} ms  {n / ms * 1e3:12.0f} playouts/s  same_result={wins == ref}", flush=True)
+            print(f"{t:40s} kernel={e.last_kernel_kind:5s} {ms:10.1f} ms  {n / ms * 1e3:12.0f} playouts/s  same_result={wins == ref} blocks_per_sm={e.kernel_info(n)['blocks_per_sm']} wins={wins}", flush=True)
 
 
 if __name__ == "__main__":
