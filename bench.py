@@ -415,12 +415,12 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            # one untimed step first, then two timed ones: the host cores are measured at their sustained clocks, as
-            # in the --impl reference arm (a single cold step ran 9 % faster than the sustained rate on the GPU box)
+            # exactly the --impl reference arm's schedule (same sample per step, same warm-up and step counts, same game ids):
+            # the host cores' clocks sag over the first ~15 s of all-core load, so a shorter leg reads 8-9 % high on the GPU box
             sample = CPU_PLAYOUTS_PER_THREAD * cores
-            cdt = cpu_rollouts(sample, cores, steps=2, warmup=1)
-            line["cpu_baseline"] = {"value": 2 * sample / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"2 steps x {sample} playouts of the same leaf after 1 warm-up step, oracle/oponn_oracle.c -O2, "
+            cdt = cpu_rollouts(sample, cores, steps=args.steps, warmup=args.warmup)
+            line["cpu_baseline"] = {"value": args.steps * sample / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.steps} steps x {sample} playouts of the same leaf after {args.warmup} warm-up steps, oracle/oponn_oracle.c -O2, "
                                               f"{cores} threads (C restatement of the Java simulator; JVM and Lux SDK unavailable)"}
     eng.close()
     if not args.no_extra:
