@@ -7,7 +7,7 @@ Lists with remove(Object) / remove(int), int arithmetic, (int) casts, Math.round
 
 Restated (O/ = /root/reference/src/com/mld46/oponn/):
   O/sim/boards/SimulationBoard.java:178-359 setupState, :365-481 simulate, :485-1015 the rules, :1076-1111 income / next player
-  O/sim/boards/ModellingBoard.java (all-SimRandom line-up: nothing observable)
+  O/sim/boards/ModellingBoard.java, O/sim/agents/SimAngry.java, SimStinky.java, MapHelper.java:132-191 (class ModellingBoard below)
   O/sim/agents/SimRandom.java (whole), O/sim/agents/SimAgent.java:122-131
   O/BattleSim.java:66-162 (the samplers; outcome tables are taken from the caller -- they have their own independent
                            restatement in tests/battlesim_ref.py)
@@ -640,6 +640,12 @@ class SimulationBoard:
                 if self.armies[defender] > 1:
                     attackers.append(defender)
 
+    def agent_fortify_phase(self):                                    # SimRandom.fortifyPhase: empty
+        pass
+
+    def setup_fortification_phase(self):                              # (:900-906) only observable through getMoveableArmies: ModellingBoard below
+        pass
+
     # ---- simulate (:365-481) -----------------------------------------------------------------------------------------------
     def step_limit_hit(self):
         if self.player_turns >= self.max_turns:
@@ -681,6 +687,7 @@ class SimulationBoard:
             self.agent_attack_phase()
             self.tear_down_attack()
         elif ph == FORTIFICATION:
+            self.agent_fortify_phase()                                # (:425: no setupFortificationPhase on the catch-up path)
             self.tear_down_fortification()
         else:
             raise JavaError("NEXT_PHASE")
@@ -717,6 +724,8 @@ class SimulationBoard:
                 self.agent_attack_phase()
                 self.tear_down_attack()
             elif ph == FORTIFICATION:
+                self.setup_fortification_phase()
+                self.agent_fortify_phase()
                 self.tear_down_fortification()
                 self.step_limit_hit()
             else:
@@ -727,9 +736,260 @@ class StepLimit(Exception):
     pass
 
 
-def play(risk_map, rules, bs, outcomes, seed: int = 0, game: int = 0, words: Optional[Sequence[int]] = None) -> dict:
+AGENT_RANDOM, AGENT_ANGRY, AGENT_STINKY = 0, 1, 2
+MAX_REDRAWS = 65536      # engine limit on SimStinky.placeArmies' rejection loop (include/orx_state.h ORX_MAX_REDRAWS)
+
+
+class ModellingBoard(SimulationBoard):
+    """O/sim/boards/ModellingBoard.java + the modelled policies O/sim/agents/SimAngry.java and SimStinky.java, written from
+    the Java.  SDK semantics (Country.getWeakestEnemyNeighbor / getNumberEnemyNeighbors / getNumberPlayerNeighbors, the
+    one-ahead CountryIterators, BoardHelper.getPlayerArmies) are the DECLARED ASSUMPTIONS of include/orx_state.h; engine
+    conventions of the same header: the agents' private `rand` objects draw from the playout's stream, a FORTIFICATION leaf
+    starts with setupFortificationPhase's moveable armies, SimStinky's redraw loop is capped."""
+
+    def __init__(self, risk_map, rules, outcomes, sim_agents: Sequence[int], modelling_turn_limit: int):
+        super().__init__(risk_map, rules, outcomes)
+        self.initial_agents = list(sim_agents)
+        self.limit = modelling_turn_limit
+
+    # ModellingBoard.setupGeneralGameState (:21-27): every setupState starts from the modelled line-up again
+    def setup_state(self, bs, stream: Stream):
+        self.agents = list(self.initial_agents)
+        super().setup_state(bs, stream)
+        fort = self.phase == FORTIFICATION
+        self.moveable = [self.armies[c] if fort and self.owner[c] == self.cp else 0 for c in range(self.N)]
+
+    def agent(self) -> int:
+        return self.agents[self.cp]
+
+    # ModellingBoard.tearDownFortificationPhase (:29-46), then SimulationBoard's (:965-982: moveable armies back to 0 first)
+    def tear_down_fortification(self):
+        nxt = self.cp
+        for _ in range(self.P + 1):
+            nxt = (nxt + 1) % self.P
+            if self.count[nxt] != 0:
+                break
+        else:
+            raise JavaError("getNextPlayer would spin forever")
+        if nxt < self.cp and self.sim_turn + 1 == self.limit:
+            self.agents = [AGENT_RANDOM] * self.P
+        self.moveable = [0] * self.N
+        super().tear_down_fortification()
+
+    def setup_fortification_phase(self):
+        self.moveable = [self.armies[c] if self.owner[c] == self.cp else 0 for c in range(self.N)]
+
+    # SimulationBoard.fortifyArmies (:908-954)
+    def fortify_armies(self, n: int, src: int, dst: int) -> int:
+        source_armies, moveable = self.armies[src], self.moveable[src]
+        if self.phase != FORTIFICATION:
+            raise JavaError("cannot fortify in this phase")
+        if self.owner[src] != self.cp or self.owner[dst] != self.cp:
+            return -1
+        if n < 0:
+            return -1
+        k = min(n, min(moveable, source_armies - 1))
+        if k == 0:
+            return 0
+        self.armies[src] = source_armies - k
+        self.moveable[src] = moveable - k
+        self.armies[dst] += k
+        return 1
+
+    # ---- Lux SDK (declared assumptions) ----------------------------------------------------------------------------------
+    def enemy_neighbors(self, cc: int) -> int:
+        return sum(1 for x in self.adj[cc] if self.owner[x] != self.owner[cc])
+
+    def player_neighbors(self, cc: int, player: int) -> int:
+        return sum(1 for x in self.adj[cc] if self.owner[x] == player)
+
+    def weakest_enemy_neighbor(self, cc: int) -> Optional[int]:
+        best = None
+        for x in self.adj[cc]:
+            if self.owner[x] != self.owner[cc] and (best is None or self.armies[x] < self.armies[best]):
+                best = x
+        return best
+
+    def country_iterator(self, player: int, armies: int = 0):
+        """PlayerIterator (armies == 0) / ArmiesIterator: code order, ONE element held ahead -- the element after `us` is looked
+        for when `us` is handed out, on the board as it is at that moment"""
+        def matches(cc):
+            if self.owner[cc] != player:
+                return False
+            if armies > 0:
+                return self.armies[cc] >= armies
+            if armies < 0:
+                return self.armies[cc] <= -armies
+            return True
+
+        def find(start):
+            for cc in range(start, self.N):
+                if matches(cc):
+                    return cc
+            return None
+
+        held = find(0)
+        while held is not None:
+            us = held
+            held = find(us + 1)
+            yield us
+
+    # ---- MapHelper (:132-191) -----------------------------------------------------------------------------------------------
+    def smallest_positive_continent(self, need_all: bool) -> int:
+        smallest_size, smallest = 2 ** 31 - 1, -1
+        for cont in range(self.C):
+            members = [cc for cc in range(self.N) if self.continent[cc] == cont]
+            free = [cc for cc in members if self.owner[cc] == -1]
+            ok = (len(free) == len(members)) if need_all else (len(free) > 0)
+            if len(members) < smallest_size and ok and self.bonus[cont] > 0:
+                smallest_size, smallest = len(members), cont
+        return smallest
+
+    # ---- SimAngry (SimAngry.java) ----------------------------------------------------------------------------------------------
+    def angry_pick_country(self) -> int:
+        me = self.cp
+        goal = self.smallest_positive_continent(True)
+        if goal == -1:
+            goal = self.smallest_positive_continent(False)
+        members = [cc for cc in range(self.N) if self.continent[cc] == goal]      # ContinentIterator: code order
+        for cc in members:
+            if self.owner[cc] == -1 and self.player_neighbors(cc, me) > 0:
+                return cc
+        best, fewest = -1, 1000000
+        for cc in members:
+            if self.owner[cc] == -1 and len(self.adj[cc]) < fewest:
+                best, fewest = cc, len(self.adj[cc])
+        return best
+
+    def angry_place(self, n: int):
+        most, place_on = -1, None
+        for us in self.country_iterator(self.cp):
+            sub = self.enemy_neighbors(us)
+            if sub > most:
+                most, place_on = sub, us
+        if place_on is None:
+            raise JavaError("placeOn.getCode() on null")
+        self.place_armies(n, place_on)
+
+    def angry_attack_phase(self):
+        made_attack = True
+        while made_attack:
+            made_attack = False
+            for us in self.country_iterator(self.cp, 2):
+                weakest = self.weakest_enemy_neighbor(us)
+                if weakest is not None and self.armies[us] > self.armies[weakest]:
+                    self.attack(us, weakest, True)
+                    made_attack = True
+
+    def angry_move_armies_in(self, cca: int, ccd: int) -> int:
+        if self.enemy_neighbors(cca) > self.enemy_neighbors(ccd):
+            return 0
+        return self.armies[cca] - 1
+
+    def angry_fortify_phase(self):
+        me = self.cp
+        for i in range(self.N):
+            if self.owner[i] == me and self.moveable[i] > 0:
+                neighbors = self.adj[i]
+                best_prospect, best_enemies = -1, 0
+                for x in neighbors:
+                    if self.owner[x] == me:
+                        e = self.enemy_neighbors(x)
+                        if e > best_enemies:
+                            best_prospect, best_enemies = x, e
+                e = self.enemy_neighbors(i)
+                if best_enemies > e:
+                    self.fortify_armies(self.moveable[i], i, best_prospect)
+                elif e == 0:
+                    rand_cc = self.rnd.nextInt(len(neighbors))
+                    self.fortify_armies(self.moveable[i], i, neighbors[rand_cc])
+
+    # ---- SimStinky (SimStinky.java) -----------------------------------------------------------------------------------------------
+    def stinky_place(self, n: int):
+        tries = 0
+        while True:
+            if tries >= MAX_REDRAWS:
+                self.flags |= FLAG_STEP_LIMIT
+                raise StepLimit()
+            tries += 1
+            test = self.rnd.nextInt(self.N)
+            if not (self.owner[test] != self.cp or self.weakest_enemy_neighbor(test) is None):
+                break
+        self.place_armies(n, test)
+
+    def stinky_attack_pass(self, care_about_odds: bool) -> bool:
+        attacked = False
+        for us in self.country_iterator(self.cp):
+            weak = self.weakest_enemy_neighbor(us)
+            if weak is not None and self.armies[us] > 1 and (self.armies[us] > self.armies[weak] * 1.5 or not care_about_odds):
+                self.attack(us, weak, True)
+                attacked = True
+        return attacked
+
+    def stinky_attack_phase(self):
+        self.stinky_attack_pass(True)
+        if sum(self.armies[cc] for cc in range(self.N) if self.owner[cc] == self.cp) > 300:
+            while self.stinky_attack_pass(False):
+                pass
+
+    def stinky_move_armies_in(self, cca: int, ccd: int) -> int:
+        attack_weak, defend_weak = self.weakest_enemy_neighbor(cca), self.weakest_enemy_neighbor(ccd)
+        if attack_weak is None:
+            return 1000000
+        if defend_weak is None:
+            return 0
+        if self.armies[attack_weak] < self.armies[defend_weak]:
+            return 0
+        return 1000000
+
+    # ---- simAgents[currentPlayer].xxx() ----------------------------------------------------------------------------------------
+    def agent_pick_country(self) -> int:
+        a = self.agent()
+        if a == AGENT_ANGRY:
+            return self.angry_pick_country()
+        if a == AGENT_STINKY:
+            return -1
+        return super().agent_pick_country()
+
+    def agent_cards_phase(self):
+        if self.agent() == AGENT_RANDOM:
+            super().agent_cards_phase()
+
+    def agent_place(self, n: int):
+        a = self.agent()
+        if a == AGENT_ANGRY:
+            self.angry_place(n)
+        elif a == AGENT_STINKY:
+            self.stinky_place(n)
+        else:
+            super().agent_place(n)
+
+    def agent_move_armies_in(self, a: int, d: int) -> int:
+        ag = self.agent()
+        if ag == AGENT_ANGRY:
+            return self.angry_move_armies_in(a, d)
+        if ag == AGENT_STINKY:
+            return self.stinky_move_armies_in(a, d)
+        return super().agent_move_armies_in(a, d)
+
+    def agent_attack_phase(self):
+        a = self.agent()
+        if a == AGENT_ANGRY:
+            self.angry_attack_phase()
+        elif a == AGENT_STINKY:
+            self.stinky_attack_phase()
+        else:
+            super().agent_attack_phase()
+
+    def agent_fortify_phase(self):
+        if self.agent() == AGENT_ANGRY:
+            self.angry_fortify_phase()
+
+
+def play(risk_map, rules, bs, outcomes, seed: int = 0, game: int = 0, words: Optional[Sequence[int]] = None,
+         sim_agents: Optional[Sequence[int]] = None, modelling_turn_limit: int = 2) -> dict:
     """one playout -> the fields of OrxGameResult"""
-    b = SimulationBoard(risk_map, rules, outcomes)
+    b = SimulationBoard(risk_map, rules, outcomes) if sim_agents is None else ModellingBoard(risk_map, rules, outcomes, sim_agents, modelling_turn_limit)
     stream = Stream(seed, game, words)
     flags = 0
     try:

@@ -31,9 +31,9 @@ def outcomes(a: int, d: int):
     return [(float(pr[i]), int(al[i]), int(dl[i])) for i in range(len(pr))]
 
 
-def compare(m, r, leaves, ppl, seed):
+def compare(m, r, leaves, ppl, seed, agents=None, limit=2):
     """pysim v oracle on every (leaf, playout); returns the number of games compared"""
-    o = Oracle(m, r)
+    o = Oracle(m, r) if agents is None else Oracle(m, r, sim_agents=agents, modelling_turn_limit=limit)
     try:
         _, want = o.rollout_batch(leaves, ppl, seed, per_game=True, threads=8)
     finally:
@@ -42,7 +42,7 @@ def compare(m, r, leaves, ppl, seed):
     for i in range(len(leaves)):
         bs = BoardState.unpack(m, leaves[i])
         for j in range(ppl):
-            got = pysim.play(m, r, bs, outcomes, seed=seed, game=i * ppl + j)
+            got = pysim.play(m, r, bs, outcomes, seed=seed, game=i * ppl + j, sim_agents=agents, modelling_turn_limit=limit)
             w = want[i * ppl + j]
             exp = dict(player_out_on_turn=[int(x) for x in w["player_out_on_turn"]], sim_turn_count=int(w["sim_turn_count"]),
                        flags=int(w["flags"]), stream_pos=int(w["stream_pos"]), board_hash=int(w["board_hash"]))
@@ -130,5 +130,48 @@ def test_hand_derived_scenarios_through_pysim():
     for make in scenarios.ALL:
         m, r, leaf, words, exp = make()
         got = pysim.play(m, r, BoardState.unpack(m, leaf.pack(m)), outcomes, words=list(words))
+        assert got["player_out_on_turn"][:m.n_players] == exp["pot"], make.__name__
+        assert (got["sim_turn_count"], got["flags"], got["stream_pos"], got["board_hash"]) == (exp["turns"], exp["flags"], exp["stream_pos"], exp["hash"]), make.__name__
+
+
+# ---- opponent modelling (row f4): ModellingBoard + SimAngry + SimStinky, restated a second time from the Java -----------------
+
+LINEUPS = [([1] * 6, 2), ([2] * 6, 2), ([0, 1, 2, 1, 2, 0], 2), ([1, 2, 0, 0, 2, 1], 1), ([2, 1, 1, 2, 1, 2], 1 << 20)]
+
+
+@pytest.mark.parametrize("agents,limit", LINEUPS, ids=lambda x: "".join(map(str, x)) if isinstance(x, list) else str(x))
+def test_modelled_opponents_every_phase(agents, limit):
+    """SimAngry / SimStinky line-ups behind ModellingBoard from every phase and attack sub-state (SimStinky cannot draft: its
+    playouts from COUNTRY_SELECTION leaves carry FLAG_ERROR in both restatements)"""
+    m = classic42(6)
+    n = 0
+    for base in (None, mid_leaf()):
+        leaves, _ = phase_zoo(m, base)
+        n += compare(m, Rules(max_player_turns=40), leaves, 2, 777, agents, limit)
+    assert n >= 80
+
+
+def test_modelled_opponents_random_maps_and_rules():
+    rng = np.random.default_rng(20261024)
+    n = 0
+    for k in range(6):
+        nt = int(rng.choice([5, 12, 33, 42, 64])); p = int(rng.integers(2, 9))
+        m = random_map(rng, nt, p, int(rng.integers(1, 9)))
+        r = Rules(use_cards=bool(rng.random() < 0.8), transfer_cards=bool(rng.integers(2)), continent_increase=int(rng.choice([0, 3])),
+                  max_player_turns=int(rng.choice([8, 16])))
+        agents = [int(x) for x in rng.integers(0, 3, size=p)]
+        n += compare(m, r, random_leaves(m, rng, 20), 1, 4321 + k, agents, int(rng.choice([1, 2, 3])))
+    assert n == 120
+
+
+def test_modelled_games_played_to_the_end():
+    assert compare(classic42(6), Rules(), mid_leaf()[None, :], 6, 20261019, [0, 1, 2, 1, 2, 1], 2) == 6
+
+
+def test_hand_derived_modelled_scenarios_through_pysim():
+    import scenarios
+    for make in scenarios.MODELLED:
+        m, r, leaf, words, exp, agents, limit = make()
+        got = pysim.play(m, r, BoardState.unpack(m, leaf.pack(m)), outcomes, words=list(words), sim_agents=agents, modelling_turn_limit=limit)
         assert got["player_out_on_turn"][:m.n_players] == exp["pot"], make.__name__
         assert (got["sim_turn_count"], got["flags"], got["stream_pos"], got["board_hash"]) == (exp["turns"], exp["flags"], exp["stream_pos"], exp["hash"]), make.__name__
