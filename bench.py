@@ -228,6 +228,8 @@ def run_extra_configs(world: int, rank: int, local: int, dev, args) -> dict:
         "note": "10,485,760 playouts per move at 8 GPUs; the per-GPU share (1,310,720) is fixed, so smaller N search fewer playouts per move"}
     tree.close()
     eng.close()
+    if rank == 0:
+        print(f"[bench] extra_configs: config 3 done ({dt:.1f} s per move at {world} GPU(s))", file=sys.stderr, flush=True)
 
     # ---- config 4: the 200-territory map ------------------------------------------------------------------------
     m4, r4 = synth200(), Rules(max_player_turns=4096)
@@ -255,6 +257,8 @@ def run_extra_configs(world: int, rank: int, local: int, dev, args) -> dict:
                      "frac": A4 * P4 / (k4 * 1e-3) / 1e9 / peak, "algorithmic_int_ops_per_playout": A4},
         "mean_rounds": float(a["len_sum"][0] / max(int(a["n"][0]), 1)), "hit_step_cap": int(a["flagged"][0])}
     eng.close()
+    if rank == 0:
+        print("[bench] extra_configs: config 4 done", file=sys.stderr, flush=True)
 
     # ---- config 5: 4,096 leaf states x 1,024 playouts, states sharded over the GPUs, no collective -----------------
     eng = RolloutEngine(m, Rules(), device=local)
